@@ -1,0 +1,531 @@
+// C-ABI implementation (include/chaos_b200.h): context, argument validation, kernel
+// dispatch, pinned host staging for the SB3 numpy contract, measurement utilities.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "kernels_common.cuh"
+
+cudaError_t cl_launch_derivatives(int kind, const void* state, const float* action, void* out,
+                                  int64_t n, cudaStream_t st);
+
+using cl::KParams;
+
+namespace {
+
+const cl_layout kLayouts[CL_ENV_KIND_COUNT] = {
+    // real_bytes n_state n_int obs act noise  act_lo act_hi  obs_lo obs_hi  max_steps
+    /* LORENZ3       */ {8, 4, 0, 6, 3, 0, -500.0, 500.0, -HUGE_VAL, HUGE_VAL, 0, 0},
+    /* LORENZ3_PAIR  */ {8, 10, 0, 6, 3, 0, -500.0, 500.0, -HUGE_VAL, HUGE_VAL, 0, 0},
+    /* LORENZ4_PAIR  */ {8, 9, 0, 8, 3, 0, -2.0, 2.0, -HUGE_VAL, HUGE_VAL, 0, 0},
+    /* HR_SYNC       */ {8, 9, 0, 6, 2, 3, -1.0, 1.0, -1.0, 1.0, 5000, 0},
+    /* PMSM_SYNC     */ {4, 9, 1, 6, 2, 3, -1.0, 1.0, -HUGE_VAL, HUGE_VAL, 2000, 0},
+    /* PMSM_CLASSIC  */ {8, 7, 0, 6, 2, 3, -2.0, 2.0, -HUGE_VAL, HUGE_VAL, 0, 0},
+    /* PMSM_SINGLE   */ {8, 4, 0, 6, 2, 0, -10.0, 10.0, -HUGE_VAL, HUGE_VAL, 0, 0},
+    /* LORENZ_RK4    */ {8, 6, 0, 6, 3, 0, -1.0, 1.0, -HUGE_VAL, HUGE_VAL, 1000, 0},
+    /* LORENZ_RK4_F32*/ {4, 6, 0, 6, 3, 0, -1.0, 1.0, -HUGE_VAL, HUGE_VAL, 1000, 0},
+    /* PMSM_RK4      */ {8, 8, 0, 6, 2, 0, -1.0, 1.0, -HUGE_VAL, HUGE_VAL, 2000, 0},
+};
+
+const int kHostRing = 3;  // pinned output slots: obs returned at step t stays valid through t+2
+
+struct HostSlot {
+  float* obs;
+  float* reward;
+  uint8_t* done;
+  float* term_obs;
+  double* last_ep_ret;
+  int32_t* last_ep_len;
+};
+
+struct HostStage {
+  bool ready;
+  float* h_act;   // pinned [N][A]
+  float* d_act;   // device [N][A]
+  float* d_obs;   // device [N][O]
+  float* d_rew;   // device [n_pad] f32
+  uint8_t* d_done;
+  float* d_term;  // device [N][O]
+  double* d_ler;
+  int32_t* d_lel;
+  HostSlot slot[kHostRing];
+  int cur;        // slot being filled / last filled
+  cudaStream_t stream;
+  bool pending;
+};
+
+}  // namespace
+
+struct cl_ctx {
+  cl_config cfg;
+  cl_layout lay;
+  char err[512];
+  uint64_t step_index;
+  int64_t launches;
+  int block;
+  int sm_count;
+  float* d_bc1;
+  float* d_bc2;
+  int bc1_n, bc2_n;
+  HostStage hs;
+};
+
+static char g_err[512] = "";
+
+static int fail(cl_ctx* ctx, int code, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(ctx, CL_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+static bool is_parity(int kind) { return kind >= CL_ENV_LORENZ3 && kind <= CL_ENV_PMSM_SINGLE; }
+
+// Threads on the most loaded SM decide the duration of a single partial wave; pick the block
+// size that minimises ceil(blocks / SMs) * block (ties -> larger block).  65,536 envs on 148
+// SMs: 64-thread blocks give 7 x 64 = 448 threads on the fullest SM vs 512 for 128 / 256.
+static int pick_block(int64_t n, int sms) {
+  const int cand[3] = {64, 128, 256};
+  int best = 256;
+  int64_t best_cost = -1;
+  for (int k = 0; k < 3; ++k) {
+    const int64_t blocks = (n + cand[k] - 1) / cand[k];
+    const int64_t cost = ((blocks + sms - 1) / sms) * cand[k];
+    if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = cand[k]; }
+  }
+  return best;
+}
+
+extern "C" int cl_abi_version(void) { return CL_ABI_VERSION; }
+
+extern "C" int cl_env_layout(int32_t kind, cl_layout* out) {
+  if (!out || kind < 0 || kind >= CL_ENV_KIND_COUNT) return fail(nullptr, CL_EINVAL, "bad kind %d", kind);
+  *out = kLayouts[kind];
+  return CL_OK;
+}
+
+extern "C" const char* cl_last_error(const cl_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+extern "C" int cl_create(const cl_config* cfg, cl_ctx** out) {
+  cl_ctx* ctx = nullptr;
+  if (!cfg || !out) return fail(nullptr, CL_EINVAL, "null argument");
+  if (cfg->abi_version != CL_ABI_VERSION) return fail(nullptr, CL_EINVAL, "abi mismatch: caller %d library %d", cfg->abi_version, CL_ABI_VERSION);
+  if (cfg->kind < 0 || cfg->kind >= CL_ENV_KIND_COUNT) return fail(nullptr, CL_EINVAL, "bad kind %d", cfg->kind);
+  if (cfg->num_envs <= 0) return fail(nullptr, CL_EINVAL, "num_envs must be > 0");
+  if (cfg->n_pad < cfg->num_envs || (cfg->n_pad % 128) != 0) return fail(nullptr, CL_EINVAL, "n_pad must be a multiple of 128 and >= num_envs");
+  if (!is_parity(cfg->kind)) {
+    if (cfg->substeps < 1 || cfg->substeps > 4096) return fail(nullptr, CL_EINVAL, "substeps out of range");
+    if (!(cfg->dt > 0.0)) return fail(nullptr, CL_EINVAL, "dt must be > 0");
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(nullptr, CL_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CL_ENODEV, "device %d out of range (%d devices)", cfg->device, ndev);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, CL_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(nullptr, CL_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+  ctx = (cl_ctx*)calloc(1, sizeof(cl_ctx));
+  if (!ctx) return fail(nullptr, CL_ENOMEM, "out of host memory");
+  ctx->cfg = *cfg;
+  ctx->lay = kLayouts[cfg->kind];
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->block = pick_block(cfg->num_envs, ctx->sm_count);
+  ctx->step_index = 0;
+  e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) { int r = fail(nullptr, CL_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); free(ctx); return r; }
+
+  if (cfg->kind == CL_ENV_PMSM_SYNC) {
+    // (float)(1 - beta**n): CPython float pow -> libm pow, then the weak-scalar rounding to
+    // float32 that NumPy applies in `self.m_t / (1 - self.beta1 ** self.adam_step)`
+    // (lorenz_env_try_pmsm.py:130-131).  The tables end where the value reaches 1.0f.
+    const double betas[2] = {0.9, 0.999};
+    float** dst[2] = {&ctx->d_bc1, &ctx->d_bc2};
+    int* cnt[2] = {&ctx->bc1_n, &ctx->bc2_n};
+    for (int k = 0; k < 2; ++k) {
+      int n = 1;
+      while ((float)(1.0 - pow(betas[k], (double)n)) != 1.0f && n < (1 << 20)) ++n;
+      float* h = (float*)malloc(sizeof(float) * (size_t)n);
+      if (!h) { free(ctx); return fail(nullptr, CL_ENOMEM, "out of host memory"); }
+      for (int j = 0; j < n; ++j) h[j] = (float)(1.0 - pow(betas[k], (double)j));
+      e = cudaMalloc((void**)dst[k], sizeof(float) * (size_t)n);
+      if (e == cudaSuccess) e = cudaMemcpy(*dst[k], h, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice);
+      free(h);
+      if (e != cudaSuccess) { int r = fail(nullptr, CL_ECUDA, "bias table upload: %s", cudaGetErrorString(e)); free(ctx); return r; }
+      *cnt[k] = n;
+    }
+  }
+  *out = ctx;
+  return CL_OK;
+}
+
+static void host_stage_free(cl_ctx* ctx) {
+  HostStage& h = ctx->hs;
+  if (!h.ready) return;
+  cudaFreeHost(h.h_act);
+  cudaFree(h.d_act); cudaFree(h.d_obs); cudaFree(h.d_rew); cudaFree(h.d_done);
+  cudaFree(h.d_term); cudaFree(h.d_ler); cudaFree(h.d_lel);
+  for (int k = 0; k < kHostRing; ++k) {
+    cudaFreeHost(h.slot[k].obs); cudaFreeHost(h.slot[k].reward); cudaFreeHost(h.slot[k].done);
+    cudaFreeHost(h.slot[k].term_obs); cudaFreeHost(h.slot[k].last_ep_ret); cudaFreeHost(h.slot[k].last_ep_len);
+  }
+  cudaStreamDestroy(h.stream);
+  h.ready = false;
+}
+
+extern "C" int cl_destroy(cl_ctx* ctx) {
+  if (!ctx) return CL_OK;
+  cudaSetDevice(ctx->cfg.device);
+  host_stage_free(ctx);
+  if (ctx->d_bc1) cudaFree(ctx->d_bc1);
+  if (ctx->d_bc2) cudaFree(ctx->d_bc2);
+  free(ctx);
+  return CL_OK;
+}
+
+static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KParams& p) {
+  if (!buf || !buf->state || !buf->ep_len || !buf->ep_return || !buf->stats)
+    return fail(ctx, CL_EINVAL, "cl_buffers: state/ep_len/ep_return/stats must be non-null");
+  if (ctx->lay.n_int > 0 && !buf->aux_int) return fail(ctx, CL_EINVAL, "cl_buffers.aux_int required for this kind");
+  memset(&p, 0, sizeof(p));
+  const cl_config& c = ctx->cfg;
+  p.n = c.num_envs; p.n_pad = c.n_pad; p.env_id_base = c.env_id_base;
+  p.k0 = (uint32_t)c.seed; p.k1 = (uint32_t)(c.seed >> 32);
+  p.step_index = ctx->step_index;
+  p.max_steps = c.max_episode_steps; p.substeps = c.substeps; p.flags = c.flags;
+  p.dt = c.dt; p.alpha = c.alpha; p.act_limit = c.act_limit; p.act_gain = c.act_gain;
+  p.param_jitter = c.param_jitter;
+  p.state = buf->state; p.aux_int = buf->aux_int; p.ep_len = buf->ep_len;
+  p.ep_return = buf->ep_return; p.stats = buf->stats;
+  p.bc1 = ctx->d_bc1; p.bc2 = ctx->d_bc2; p.bc1_n = ctx->bc1_n; p.bc2_n = ctx->bc2_n;
+  if (io) {
+    p.action = io->action; p.act_es = io->act_es; p.act_cs = io->act_cs;
+    p.noise = io->noise;
+    p.obs = io->obs; p.obs_es = io->obs_es; p.obs_cs = io->obs_cs;
+    p.reward = io->reward; p.done = io->done; p.term_obs = io->term_obs;
+    p.last_ep_ret = io->last_ep_ret; p.last_ep_len = io->last_ep_len; p.mask = io->mask;
+  }
+  return CL_OK;
+}
+
+static int launch(cl_ctx* ctx, const KParams& p, int mode, cudaStream_t st) {
+  cudaError_t e = is_parity(ctx->cfg.kind) ? cl_launch_parity(ctx->cfg.kind, p, mode, st, ctx->block)
+                                           : cl_launch_northstar(ctx->cfg.kind, p, mode, st, ctx->block);
+  if (e != cudaSuccess) return fail(ctx, CL_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  ctx->launches += 1;
+  return CL_OK;
+}
+
+extern "C" int cl_init_persistent(cl_ctx* ctx, void* stream, const cl_buffers* buf) {
+  if (!ctx) return fail(nullptr, CL_EINVAL, "null ctx");
+  KParams p;
+  int r = fill_params(ctx, buf, nullptr, p);
+  if (r) return r;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaMemsetAsync(buf->stats, 0, sizeof(double) * CL_NSTATS, (cudaStream_t)stream));
+  return launch(ctx, p, cl::MODE_INIT, (cudaStream_t)stream);
+}
+
+extern "C" int cl_reset(cl_ctx* ctx, void* stream, const cl_buffers* buf, const cl_io* io) {
+  if (!ctx) return fail(nullptr, CL_EINVAL, "null ctx");
+  KParams p;
+  int r = fill_params(ctx, buf, io, p);
+  if (r) return r;
+  CU(cudaSetDevice(ctx->cfg.device));
+  r = launch(ctx, p, cl::MODE_RESET, (cudaStream_t)stream);
+  if (r == CL_OK) ctx->step_index += 1;
+  return r;
+}
+
+extern "C" int cl_step(cl_ctx* ctx, void* stream, const cl_buffers* buf, const cl_io* io) {
+  if (!ctx) return fail(nullptr, CL_EINVAL, "null ctx");
+  if (!io || !io->action) return fail(ctx, CL_EINVAL, "cl_step: io.action is required");
+  KParams p;
+  int r = fill_params(ctx, buf, io, p);
+  if (r) return r;
+  p.reward_f32 = 0;
+  CU(cudaSetDevice(ctx->cfg.device));
+  r = launch(ctx, p, cl::MODE_STEP, (cudaStream_t)stream);
+  if (r == CL_OK) ctx->step_index += 1;
+  return r;
+}
+
+extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, const cl_io* io,
+                          const cl_rollout_desc* d) {
+  if (!ctx) return fail(nullptr, CL_EINVAL, "null ctx");
+  if (!io || !d || d->T < 1) return fail(ctx, CL_EINVAL, "cl_rollout: io/desc required, T >= 1");
+  if (io->noise) return fail(ctx, CL_EINVAL, "cl_rollout: noise override is single-step only");
+  KParams p;
+  int r = fill_params(ctx, buf, io, p);
+  if (r) return r;
+  p.T = d->T; p.act_ts = d->act_ts; p.obs_ts = d->obs_ts; p.rew_ts = d->rew_ts; p.done_ts = d->done_ts;
+  p.synth_amp = (float)d->synth_amp;
+  CU(cudaSetDevice(ctx->cfg.device));
+  r = launch(ctx, p, cl::MODE_ROLLOUT, (cudaStream_t)stream);
+  if (r == CL_OK) ctx->step_index += (uint64_t)d->T;
+  return r;
+}
+
+extern "C" int cl_derivatives(cl_ctx* ctx, void* stream, const void* state, const float* action,
+                              void* out, int64_t n) {
+  if (!ctx || !state || !out || n <= 0) return fail(ctx, CL_EINVAL, "cl_derivatives: bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  cudaError_t e = cl_launch_derivatives(ctx->cfg.kind, state, action, out, n, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(ctx, CL_ECUDA, "cl_derivatives: %s", cudaGetErrorString(e));
+  ctx->launches += 1;
+  return CL_OK;
+}
+
+extern "C" int cl_stats(cl_ctx* ctx, void* stream, const cl_buffers* buf, double* out8, int clear) {
+  if (!ctx || !buf || !buf->stats || !out8) return fail(ctx, CL_EINVAL, "cl_stats: bad argument");
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaMemcpyAsync(out8, buf->stats, sizeof(double) * CL_NSTATS, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (clear) CU(cudaMemsetAsync(buf->stats, 0, sizeof(double) * CL_NSTATS, (cudaStream_t)stream));
+  return CL_OK;
+}
+
+extern "C" int cl_get_step_index(const cl_ctx* ctx, uint64_t* out) {
+  if (!ctx || !out) return CL_EINVAL;
+  *out = ctx->step_index;
+  return CL_OK;
+}
+extern "C" int cl_set_step_index(cl_ctx* ctx, uint64_t v) {
+  if (!ctx) return CL_EINVAL;
+  ctx->step_index = v;
+  return CL_OK;
+}
+extern "C" int64_t cl_launch_count(const cl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int cl_block_size(const cl_ctx* ctx) { return ctx ? ctx->block : 0; }
+
+// ---- host-buffer path ------------------------------------------------------------------
+
+static int host_stage_init(cl_ctx* ctx) {
+  HostStage& h = ctx->hs;
+  if (h.ready) return CL_OK;
+  const size_t N = (size_t)ctx->cfg.num_envs, NP = (size_t)ctx->cfg.n_pad;
+  const size_t A = (size_t)ctx->lay.act_dim, O = (size_t)ctx->lay.obs_dim;
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
+  CU(cudaHostAlloc((void**)&h.h_act, N * A * sizeof(float), cudaHostAllocDefault));
+  CU(cudaMalloc((void**)&h.d_act, N * A * sizeof(float)));
+  CU(cudaMalloc((void**)&h.d_obs, N * O * sizeof(float)));
+  CU(cudaMalloc((void**)&h.d_rew, NP * sizeof(float)));
+  CU(cudaMalloc((void**)&h.d_done, NP));
+  CU(cudaMalloc((void**)&h.d_term, N * O * sizeof(float)));
+  CU(cudaMalloc((void**)&h.d_ler, NP * sizeof(double)));
+  CU(cudaMalloc((void**)&h.d_lel, NP * sizeof(int32_t)));
+  CU(cudaMemset(h.d_term, 0, N * O * sizeof(float)));
+  CU(cudaMemset(h.d_ler, 0, NP * sizeof(double)));
+  CU(cudaMemset(h.d_lel, 0, NP * sizeof(int32_t)));
+  for (int k = 0; k < kHostRing; ++k) {
+    CU(cudaHostAlloc((void**)&h.slot[k].obs, N * O * sizeof(float), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&h.slot[k].reward, N * sizeof(float), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&h.slot[k].done, N, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&h.slot[k].term_obs, N * O * sizeof(float), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&h.slot[k].last_ep_ret, N * sizeof(double), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&h.slot[k].last_ep_len, N * sizeof(int32_t), cudaHostAllocDefault));
+  }
+  h.cur = 0;
+  h.pending = false;
+  h.ready = true;
+  return CL_OK;
+}
+
+static cudaStream_t host_stream(cl_ctx* ctx, void* stream) {
+  // stream == (void*)-1 selects the context's own non-blocking stream
+  return stream == (void*)(intptr_t)-1 ? ctx->hs.stream : (cudaStream_t)stream;
+}
+
+extern "C" int cl_host_action_staging(cl_ctx* ctx, float** act) {
+  if (!ctx || !act) return fail(ctx, CL_EINVAL, "bad argument");
+  int r = host_stage_init(ctx);
+  if (r) return r;
+  *act = ctx->hs.h_act;
+  return CL_OK;
+}
+
+extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* buf, const float* action_host) {
+  if (!ctx) return fail(nullptr, CL_EINVAL, "null ctx");
+  int r = host_stage_init(ctx);
+  if (r) return r;
+  HostStage& h = ctx->hs;
+  if (h.pending) return fail(ctx, CL_EINVAL, "cl_step_host_async called twice without cl_step_host_wait");
+  const size_t N = (size_t)ctx->cfg.num_envs;
+  const size_t A = (size_t)ctx->lay.act_dim, O = (size_t)ctx->lay.obs_dim;
+  cudaStream_t st = host_stream(ctx, stream);
+  if (action_host && action_host != h.h_act) memcpy(h.h_act, action_host, N * A * sizeof(float));
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaMemcpyAsync(h.d_act, h.h_act, N * A * sizeof(float), cudaMemcpyHostToDevice, st));
+  cl_io io;
+  memset(&io, 0, sizeof(io));
+  io.action = h.d_act; io.act_es = (int64_t)A; io.act_cs = 1;
+  io.obs = h.d_obs; io.obs_es = (int64_t)O; io.obs_cs = 1;
+  io.reward = h.d_rew; io.done = h.d_done; io.term_obs = h.d_term;
+  io.last_ep_ret = h.d_ler; io.last_ep_len = h.d_lel;
+  KParams p;
+  r = fill_params(ctx, buf, &io, p);
+  if (r) return r;
+  p.reward_f32 = 1;
+  p.flags &= ~CL_F_OBS_F64;
+  r = launch(ctx, p, cl::MODE_STEP, st);
+  if (r) return r;
+  ctx->step_index += 1;
+  h.cur = (h.cur + 1) % kHostRing;
+  HostSlot& s = h.slot[h.cur];
+  CU(cudaMemcpyAsync(s.obs, h.d_obs, N * O * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(s.reward, h.d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(s.done, h.d_done, N, cudaMemcpyDeviceToHost, st));
+  h.pending = true;
+  return CL_OK;
+}
+
+
+
+static int host_wait_common(cl_ctx* ctx, void* stream, int64_t* n_done_out) {
+  HostStage& h = ctx->hs;
+  if (!h.ready || !h.pending) return fail(ctx, CL_EINVAL, "cl_step_host_wait without a pending cl_step_host_async");
+  cudaStream_t st = host_stream(ctx, stream);
+  CU(cudaSetDevice(ctx->cfg.device));
+  CU(cudaStreamSynchronize(st));
+  h.pending = false;
+  const size_t N = (size_t)ctx->cfg.num_envs, O = (size_t)ctx->lay.obs_dim;
+  HostSlot& s = h.slot[h.cur];
+  int64_t nd = 0;
+  for (size_t i = 0; i < N; ++i) nd += (s.done[i] != 0);
+  if (nd > 0) {  // rare: fetch the terminal observations and Monitor numbers
+    CU(cudaMemcpyAsync(s.term_obs, h.d_term, N * O * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s.last_ep_ret, h.d_ler, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(s.last_ep_len, h.d_lel, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  *n_done_out = nd;
+  return CL_OK;
+}
+
+extern "C" int cl_step_host_wait_view(cl_ctx* ctx, void* stream, cl_host_view* v) {
+  if (!ctx || !v) return fail(ctx, CL_EINVAL, "bad argument");
+  int64_t nd = 0;
+  int r = host_wait_common(ctx, stream, &nd);
+  if (r) return r;
+  HostSlot& s = ctx->hs.slot[ctx->hs.cur];
+  v->obs = s.obs; v->reward = s.reward; v->done = s.done; v->term_obs = s.term_obs;
+  v->last_ep_ret = s.last_ep_ret; v->last_ep_len = s.last_ep_len; v->n_done = nd;
+  return CL_OK;
+}
+
+extern "C" int cl_step_host_wait(cl_ctx* ctx, void* stream, float* obs_host, float* reward_host,
+                                 uint8_t* done_host, float* term_obs_host, double* last_ep_ret_host,
+                                 int32_t* last_ep_len_host, int64_t* n_done) {
+  if (!ctx) return fail(nullptr, CL_EINVAL, "null ctx");
+  int64_t nd = 0;
+  int r = host_wait_common(ctx, stream, &nd);
+  if (r) return r;
+  const size_t N = (size_t)ctx->cfg.num_envs, O = (size_t)ctx->lay.obs_dim;
+  HostSlot& s = ctx->hs.slot[ctx->hs.cur];
+  if (obs_host) memcpy(obs_host, s.obs, N * O * sizeof(float));
+  if (reward_host) memcpy(reward_host, s.reward, N * sizeof(float));
+  if (done_host) memcpy(done_host, s.done, N);
+  if (nd > 0) {
+    if (term_obs_host) memcpy(term_obs_host, s.term_obs, N * O * sizeof(float));
+    if (last_ep_ret_host) memcpy(last_ep_ret_host, s.last_ep_ret, N * sizeof(double));
+    if (last_ep_len_host) memcpy(last_ep_len_host, s.last_ep_len, N * sizeof(int32_t));
+  }
+  if (n_done) *n_done = nd;
+  return CL_OK;
+}
+
+extern "C" int cl_reset_host(cl_ctx* ctx, void* stream, const cl_buffers* buf, float* obs_host) {
+  if (!ctx || !obs_host) return fail(ctx, CL_EINVAL, "bad argument");
+  int r = host_stage_init(ctx);
+  if (r) return r;
+  HostStage& h = ctx->hs;
+  const size_t N = (size_t)ctx->cfg.num_envs, O = (size_t)ctx->lay.obs_dim;
+  cudaStream_t st = host_stream(ctx, stream);
+  cl_io io;
+  memset(&io, 0, sizeof(io));
+  io.obs = h.d_obs; io.obs_es = (int64_t)O; io.obs_cs = 1;
+  KParams p;
+  r = fill_params(ctx, buf, &io, p);
+  if (r) return r;
+  p.flags &= ~CL_F_OBS_F64;
+  CU(cudaSetDevice(ctx->cfg.device));
+  r = launch(ctx, p, cl::MODE_RESET, st);
+  if (r) return r;
+  ctx->step_index += 1;
+  h.cur = (h.cur + 1) % kHostRing;
+  CU(cudaMemcpyAsync(h.slot[h.cur].obs, h.d_obs, N * O * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  memcpy(obs_host, h.slot[h.cur].obs, N * O * sizeof(float));
+  return CL_OK;
+}
+
+extern "C" int64_t cl_host_h2d_bytes(const cl_ctx* ctx) {
+  return ctx ? ctx->cfg.num_envs * ctx->lay.act_dim * (int64_t)sizeof(float) : 0;
+}
+extern "C" int64_t cl_host_d2h_bytes(const cl_ctx* ctx) {
+  return ctx ? ctx->cfg.num_envs * (ctx->lay.obs_dim * (int64_t)sizeof(float) + (int64_t)sizeof(float) + 1) : 0;
+}
+
+// ---- measurement -----------------------------------------------------------------------
+
+extern "C" int cl_measure_fma_peak(int32_t device, int32_t dtype_bytes, double seconds, double* tflops) {
+  cl_ctx* ctx = nullptr;
+  if (!tflops || (dtype_bytes != 8 && dtype_bytes != 4)) return fail(nullptr, CL_EINVAL, "bad argument");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int block = 256, grid = prop.multiProcessorCount * 8;
+  void* sink = nullptr;
+  CU(cudaMalloc(&sink, 64));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  int iters = 2000;
+  double best = 0.0, spent = 0.0;
+  // warm-up + adaptive repetition: best of the launches that fit in `seconds`
+  for (int rep = 0; rep < 64; ++rep) {
+    CU(cudaEventRecord(e0, 0));
+    CU(cl_fma_peak_launch(dtype_bytes, grid, block, iters, sink, 0));
+    CU(cudaEventRecord(e1, 0));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8.0 * 16.0 * (double)iters * (double)grid * (double)block;
+    const double tf = fl / ((double)ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+    if (rep > 0) spent += (double)ms * 1e-3;
+    if (ms < 20.f) iters *= 2;
+    if (spent >= seconds && rep >= 3) break;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops = best;
+  return CL_OK;
+}
+
+// ---- host-side test hooks ----------------------------------------------------------------
+
+extern "C" void cl_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  cl::u32x4 c;
+  c.x = ctr[0]; c.y = ctr[1]; c.z = ctr[2]; c.w = ctr[3];
+  const cl::u32x4 r = cl::philox4x32_10(c, key[0], key[1]);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+extern "C" double cl_uniform53(uint32_t a, uint32_t b, double lo, double hi) {
+  return cl::uniform53(a, b, lo, hi);
+}

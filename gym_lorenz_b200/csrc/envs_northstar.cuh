@@ -1,0 +1,191 @@
+// North-star env kinds (BASELINE.json north_star; SURVEY.md section 0 "D1-D3" and 8d):
+// classical RK4 with S substeps per control interval, zero-order-hold control added to the
+// derivative, per-env parameters held in registers next to the state.  These kinds have no
+// counterpart class in the reference (its Lorenz envs are Euler x 1, dynamic.py:70-75);
+// they keep dynamic.py's observation / reward / action contract and are validated against
+// adaptive integration (scipy DOP853, rtol 1e-13) per control interval at rtol 1e-9.
+//
+// Compiled into tu_northstar.cu with FMA contraction ON: per RHS evaluation 7 FMA-pipe
+// instructions, per RK4 substep 49 (28 RHS + 9 stage + 12 combine) = 87 algorithmic flop.
+#pragma once
+#include "kernels_common.cuh"
+
+namespace cl {
+
+template <typename R>
+struct LorenzPar { R sigma, rho, beta; };
+
+// f(s) + u : dx = sigma (y - x) + u1 ; dy = x (rho - z) - y + u2 ; dz = x y - beta z + u3
+template <typename R>
+__device__ __forceinline__ void lorenz_rhs_u(const LorenzPar<R>& q, R x, R y, R z, R u1, R u2, R u3,
+                                             R& dx, R& dy, R& dz) {
+  dx = fma(q.sigma, y - x, u1);
+  dy = fma(x, q.rho - z, u2 - y);
+  dz = fma(x, y, fma(-q.beta, z, u3));
+}
+
+template <typename R>
+__device__ __forceinline__ void lorenz_rk4(const LorenzPar<R>& q, R& x, R& y, R& z, R u1, R u2, R u3,
+                                           R h, int substeps) {
+  const R hh = R(0.5) * h, h6 = h / R(6), h3 = h / R(3);
+#pragma unroll 2
+  for (int k = 0; k < substeps; ++k) {
+    R k1x, k1y, k1z, kx, ky, kz, ax, ay, az;
+    lorenz_rhs_u(q, x, y, z, u1, u2, u3, k1x, k1y, k1z);
+    ax = fma(h6, k1x, x); ay = fma(h6, k1y, y); az = fma(h6, k1z, z);
+    lorenz_rhs_u(q, fma(hh, k1x, x), fma(hh, k1y, y), fma(hh, k1z, z), u1, u2, u3, kx, ky, kz);
+    ax = fma(h3, kx, ax); ay = fma(h3, ky, ay); az = fma(h3, kz, az);
+    lorenz_rhs_u(q, fma(hh, kx, x), fma(hh, ky, y), fma(hh, kz, z), u1, u2, u3, k1x, k1y, k1z);
+    ax = fma(h3, k1x, ax); ay = fma(h3, k1y, ay); az = fma(h3, k1z, az);
+    lorenz_rhs_u(q, fma(h, k1x, x), fma(h, k1y, y), fma(h, k1z, z), u1, u2, u3, kx, ky, kz);
+    x = fma(h6, kx, ax); y = fma(h6, ky, ay); z = fma(h6, kz, az);
+  }
+}
+
+// CL_ENV_LORENZ_RK4 / _F32.  planes: x y z sigma rho beta
+template <typename R>
+struct EnvLorenzRK4 {
+  typedef R real;
+  enum { NSTATE = 6, NINT = 0, OBS = 6, ACT = 3, NOISE = 0 };
+  struct S { R x, y, z; LorenzPar<R> q; };
+  __device__ static void load(S& s, const KParams& p, int64_t i) {
+    s.x = ldp<R>(p, 0, i); s.y = ldp<R>(p, 1, i); s.z = ldp<R>(p, 2, i);
+    s.q.sigma = ldp<R>(p, 3, i); s.q.rho = ldp<R>(p, 4, i); s.q.beta = ldp<R>(p, 5, i);
+  }
+  __device__ static void store(const S& s, const KParams& p, int64_t i) {
+    stp<R>(p, 0, i, s.x); stp<R>(p, 1, i, s.y); stp<R>(p, 2, i, s.z);
+    stp<R>(p, 3, i, s.q.sigma); stp<R>(p, 4, i, s.q.rho); stp<R>(p, 5, i, s.q.beta);
+  }
+  __device__ static bool uses_noise(const KParams&) { return false; }
+  __device__ static bool finite(const S& s) { return isfinite(s.x + s.y + s.z); }
+  __device__ static bool time_limit(const KParams& p, int32_t n) {
+    return p.max_steps > 0 && n >= p.max_steps;
+  }
+  // nominal (10, 28, 8/3) as dynamic.py:31-33, optionally jittered per env (new)
+  __device__ static void init_persistent(S& s, const KParams& p, const Stream& rng) {
+    double j[3] = {1.0, 1.0, 1.0};
+    if (p.param_jitter > 0.0) draw_uniform<3>(rng, TAG_PARAM, 1.0 - p.param_jitter, 1.0 + p.param_jitter, j);
+    s.q.sigma = (R)(10.0 * j[0]); s.q.rho = (R)(28.0 * j[1]); s.q.beta = (R)((8.0 / 3.0) * j[2]);
+    s.x = s.y = s.z = R(0);
+  }
+  __device__ static void observe(const S& s, R* obs) {
+    obs[0] = s.x; obs[1] = s.y; obs[2] = s.z;
+    lorenz_rhs_u(s.q, s.x, s.y, s.z, R(0), R(0), R(0), obs[3], obs[4], obs[5]);
+  }
+  __device__ static void reset(S& s, const KParams&, const Stream& rng, R* obs) {
+    double u[3];
+    draw_uniform<3>(rng, TAG_RESET, -30.0, 30.0, u);  // dynamic.py:37
+    s.x = (R)u[0]; s.y = (R)u[1]; s.z = (R)u[2];
+    observe(s, obs);
+  }
+  __device__ static void step(S& s, const KParams& p, const float* a, const double*, R* obs, R& rew,
+                              bool& term) {
+    const float lim = (float)p.act_limit;
+    const R g = (R)p.act_gain;
+    const R u1 = (R)clipf(a[0], -lim, lim) * g;
+    const R u2 = (R)clipf(a[1], -lim, lim) * g;
+    const R u3 = (R)clipf(a[2], -lim, lim) * g;
+    const R h = (R)(p.dt / (double)p.substeps);
+    lorenz_rk4<R>(s.q, s.x, s.y, s.z, u1, u2, u3, h, p.substeps);
+    observe(s, obs);
+    const R e = fabs(s.x) + fabs(s.y) + fabs(s.z);
+    rew = -e;                      // dynamic.py:84
+    term = !(e <= R(1e6));         // blow-up / NaN guard (lorenz_env_transient.py:369 `reward < -1e6`)
+  }
+};
+
+// ------------------------------------------------------------------------------------
+// CL_ENV_PMSM_RK4 (f64).  Master/slave chaotic PMSM pair (lorenz_env_try_pmsm.py:51-58
+// dynamics), RK4 x S, control clip(a, +-1) * gain on slave dx1, dx2, per-env sigma / gamma.
+// planes: a0 a1 a2  b0 b1 b2  sigma gamma
+struct PMSMPar { double sigma, gamma; };
+
+__device__ __forceinline__ void pmsm_rhs_u(const PMSMPar& q, const double* x, double u1, double u2,
+                                           double* d) {
+  d[0] = fma(x[1], x[2], u1 - x[0]);
+  d[1] = fma(q.gamma - x[0], x[2], u2 - x[1]);
+  d[2] = q.sigma * (x[1] - x[2]);
+}
+
+__device__ __forceinline__ void pmsm_rk4(const PMSMPar& q, double* x, double u1, double u2, double h,
+                                         int substeps) {
+  const double hh = 0.5 * h, h6 = h / 6.0, h3 = h / 3.0;
+#pragma unroll 2
+  for (int k = 0; k < substeps; ++k) {
+    double k1[3], k2[3], w[3], acc[3];
+    pmsm_rhs_u(q, x, u1, u2, k1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { acc[c] = fma(h6, k1[c], x[c]); w[c] = fma(hh, k1[c], x[c]); }
+    pmsm_rhs_u(q, w, u1, u2, k2);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { acc[c] = fma(h3, k2[c], acc[c]); w[c] = fma(hh, k2[c], x[c]); }
+    pmsm_rhs_u(q, w, u1, u2, k1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { acc[c] = fma(h3, k1[c], acc[c]); w[c] = fma(h, k1[c], x[c]); }
+    pmsm_rhs_u(q, w, u1, u2, k2);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[c] = fma(h6, k2[c], acc[c]);
+  }
+}
+
+struct EnvPMSMRK4 {
+  typedef double real;
+  enum { NSTATE = 8, NINT = 0, OBS = 6, ACT = 2, NOISE = 0 };
+  struct S { double a[3], b[3]; PMSMPar q; };
+  __device__ static void load(S& s, const KParams& p, int64_t i) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { s.a[c] = ldp<double>(p, c, i); s.b[c] = ldp<double>(p, 3 + c, i); }
+    s.q.sigma = ldp<double>(p, 6, i); s.q.gamma = ldp<double>(p, 7, i);
+  }
+  __device__ static void store(const S& s, const KParams& p, int64_t i) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { stp<double>(p, c, i, s.a[c]); stp<double>(p, 3 + c, i, s.b[c]); }
+    stp<double>(p, 6, i, s.q.sigma); stp<double>(p, 7, i, s.q.gamma);
+  }
+  __device__ static bool uses_noise(const KParams&) { return false; }
+  __device__ static bool finite(const S& s) {
+    return isfinite(s.a[0] + s.a[1] + s.a[2] + s.b[0] + s.b[1] + s.b[2]);
+  }
+  __device__ static bool time_limit(const KParams& p, int32_t n) {
+    return p.max_steps > 0 && n >= p.max_steps;
+  }
+  __device__ static void init_persistent(S& s, const KParams& p, const Stream& rng) {
+    double j[2] = {1.0, 1.0};
+    if (p.param_jitter > 0.0) draw_uniform<2>(rng, TAG_PARAM, 1.0 - p.param_jitter, 1.0 + p.param_jitter, j);
+    s.q.sigma = 5.46 * j[0];  // lorenz_env_try_pmsm.py:12-13
+    s.q.gamma = 20.0 * j[1];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { s.a[c] = 0.0; s.b[c] = 0.0; }
+  }
+  __device__ static void observe(const S& s, double* obs) {
+    double da[3], db[3];
+    pmsm_rhs_u(s.q, s.a, 0.0, 0.0, da);
+    pmsm_rhs_u(s.q, s.b, 0.0, 0.0, db);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { obs[c] = s.a[c] - s.b[c]; obs[3 + c] = da[c] - db[c]; }
+  }
+  __device__ static void reset(S& s, const KParams&, const Stream& rng, double* obs) {
+    double u[6];
+    draw_uniform<6>(rng, TAG_RESET, -30.0, 30.0, u);  // lorenz_env_try_pmsm.py:64-65
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { s.a[c] = u[c]; s.b[c] = u[3 + c]; }
+    observe(s, obs);
+  }
+  __device__ static void step(S& s, const KParams& p, const float* a, const double*, double* obs,
+                              double& rew, bool& term) {
+    const float lim = (float)p.act_limit;
+    const double u1 = (double)clipf(a[0], -lim, lim) * p.act_gain;
+    const double u2 = (double)clipf(a[1], -lim, lim) * p.act_gain;
+    const double h = p.dt / (double)p.substeps;
+    pmsm_rk4(s.q, s.a, 0.0, 0.0, h, p.substeps);
+    pmsm_rk4(s.q, s.b, u1, u2, h, p.substeps);
+    observe(s, obs);
+    const double e0 = fabs(obs[0]), e1 = fabs(obs[1]), e2 = fabs(obs[2]);
+    const double E = e0 + e1 + e2;
+    rew = -E - (pow(e0 + 1e-6, p.alpha) + pow(e1 + 1e-6, p.alpha) + pow(e2 + 1e-6, p.alpha));
+    term = false;
+    if (!(E <= 1000.0)) { rew = -1000.0; term = true; }  // lorenz_env_try_pmsm.py:174-176
+  }
+};
+
+}  // namespace cl

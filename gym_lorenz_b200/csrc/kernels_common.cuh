@@ -1,0 +1,293 @@
+// Generic one-thread-per-env kernels: step / fused rollout / reset / init.
+//
+// Every env kind is a small struct (`E`) giving the register-resident state `E::S`, its
+// SoA load/store, `reset`, `step` and a few predicates; the kernels below add what is
+// common to all kinds: action fetch (strided, or in-kernel Philox for synthetic
+// rollouts), process-noise draws, TimeLimit, SB3-style auto-reset, Monitor-style episode
+// accounting and warp-reduced statistics.  State stays in registers across all T control
+// intervals (and all RK4 substeps) of a launch.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/chaos_b200.h"
+#include "philox.cuh"
+
+namespace cl {
+
+struct KParams {
+  int64_t n, n_pad, env_id_base;
+  uint32_t k0, k1;
+  uint64_t step_index;
+  int32_t max_steps, substeps, flags, reward_f32;
+  double dt, alpha, act_limit, act_gain, param_jitter;
+  // persistent buffers
+  void* state;
+  int32_t* aux_int;
+  int32_t* ep_len;
+  double* ep_return;
+  double* stats;
+  // io
+  const float* action;
+  int64_t act_es, act_cs;
+  const double* noise;
+  void* obs;
+  int64_t obs_es, obs_cs;
+  void* reward;
+  uint8_t* done;
+  void* term_obs;
+  double* last_ep_ret;
+  int32_t* last_ep_len;
+  const uint8_t* mask;
+  // rollout
+  int32_t T;
+  int64_t act_ts, obs_ts, rew_ts, done_ts;
+  float synth_amp;
+  // PMSM_SYNC Adam bias-correction tables: tabK[n] = (float)(1 - betaK**n), see chaos_b200.cu
+  const float* bc1;
+  const float* bc2;
+  int32_t bc1_n, bc2_n;
+};
+
+enum LaunchMode { MODE_STEP = 0, MODE_ROLLOUT = 1, MODE_RESET = 2, MODE_INIT = 3 };
+
+// ---- small numeric helpers -----------------------------------------------------------
+
+// np.clip semantics (NaN propagates: both comparisons are false).
+__device__ __forceinline__ float clipf(float a, float lo, float hi) {
+  return a < lo ? lo : (a > hi ? hi : a);
+}
+__device__ __forceinline__ double clipd(double a, double lo, double hi) {
+  return a < lo ? lo : (a > hi ? hi : a);
+}
+
+__device__ __forceinline__ Stream make_stream(const KParams& p, int64_t i, uint64_t step) {
+  const uint64_t gid = (uint64_t)(p.env_id_base + i);
+  Stream s;
+  s.id_lo = (uint32_t)gid;
+  s.id_hi = (uint32_t)(gid >> 32);
+  s.step = (uint32_t)step;
+  // upper 24 bits of a 56-bit step counter ride in the tag word (see Stream::draw callers)
+  s.k0 = p.k0;
+  s.k1 = p.k1 ^ (uint32_t)((step >> 32) & 0x00FFFFFFu);
+  return s;
+}
+
+// n uniforms in [lo,hi) (NumPy construction), 2 per Philox block.
+template <int N>
+__device__ __forceinline__ void draw_uniform(const Stream& rng, uint32_t tag, double lo, double hi,
+                                             double* out) {
+#pragma unroll
+  for (int b = 0; b < (N + 1) / 2; ++b) {
+    const u32x4 r = rng.draw(tag + (uint32_t)b);
+    out[2 * b] = uniform53(r.x, r.y, lo, hi);
+    if (2 * b + 1 < N) out[2 * b + 1] = uniform53(r.z, r.w, lo, hi);
+  }
+}
+
+// n standard normals (Box-Muller on 53-bit uniforms), 2 per Philox block.
+template <int N>
+__device__ __forceinline__ void draw_normal(const Stream& rng, uint32_t tag, double* out) {
+#pragma unroll
+  for (int b = 0; b < (N + 1) / 2; ++b) {
+    const u32x4 r = rng.draw(tag + (uint32_t)b);
+    const double u1 = 1.0 - u01_53(r.x, r.y);  // (0,1]
+    const double u2 = u01_53(r.z, r.w);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    out[2 * b] = rad * cs;
+    if (2 * b + 1 < N) out[2 * b + 1] = rad * sn;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename real>
+__device__ __forceinline__ void store_obs(void* base, int64_t off, int64_t es, int64_t cs, int64_t i,
+                                          const real* obs, int n, bool f64) {
+  if (f64) {
+    double* o = (double*)base + off + i * es;
+    for (int c = 0; c < n; ++c) o[c * cs] = (double)obs[c];
+  } else {
+    float* o = (float*)base + off + i * es;
+    for (int c = 0; c < n; ++c) o[c * cs] = (float)obs[c];
+  }
+}
+
+// ---- the step / rollout kernel ---------------------------------------------------------
+
+template <class E, bool ROLL>
+__global__ void __launch_bounds__(256) k_step(const KParams p) {
+  typedef typename E::real real;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < p.n;
+  const unsigned lane = threadIdx.x & 31u;
+
+  typename E::S s = {};
+  int32_t ep_len = 0;
+  double ep_ret = 0.0;
+  if (live) {
+    E::load(s, p, i);
+    ep_len = p.ep_len[i];
+    ep_ret = p.ep_return[i];
+  }
+  const bool obs64 = (p.flags & CL_F_OBS_F64) != 0;
+  const bool autoreset = (p.flags & CL_F_AUTORESET) != 0;
+  const bool want_noise = E::NOISE > 0 && E::uses_noise(p);
+  const int T = ROLL ? p.T : 1;
+
+  for (int t = 0; t < T; ++t) {
+    const uint64_t step = p.step_index + (uint64_t)t;
+    const Stream rng = make_stream(p, i, step);
+
+    float a[E::ACT];
+    if (ROLL && p.action == nullptr) {
+      const u32x4 r = rng.draw(TAG_ACTION);
+      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int c = 0; c < E::ACT; ++c) a[c] = p.synth_amp * (2.0f * u01_24(w[c & 3]) - 1.0f);
+    } else {
+#pragma unroll
+      for (int c = 0; c < E::ACT; ++c)
+        a[c] = live ? p.action[(ROLL ? t * p.act_ts : 0) + i * p.act_es + c * p.act_cs] : 0.0f;
+    }
+
+    double nz[E::NOISE > 0 ? E::NOISE : 1];
+    nz[0] = 0.0;
+    if (want_noise) {
+      if (p.noise != nullptr) {
+#pragma unroll
+        for (int c = 0; c < E::NOISE; ++c) nz[c] = live ? p.noise[c * p.n_pad + i] : 0.0;
+      } else {
+        draw_normal<(E::NOISE > 0 ? E::NOISE : 1)>(rng, TAG_NOISE, nz);
+      }
+    }
+
+    real obs[E::OBS];
+    real rew;
+    bool term;
+    E::step(s, p, a, nz, obs, rew, term);
+    ep_len += 1;
+    ep_ret += (double)rew;
+    const bool trunc = E::time_limit(p, ep_len);
+    const bool done = term || trunc;
+    const bool bad = !E::finite(s);
+
+    // warp-aggregated statistics (one set of atomics per warp, only when something ended)
+    const unsigned dm = __ballot_sync(0xffffffffu, live && done && autoreset);
+    const unsigned bm = __ballot_sync(0xffffffffu, live && bad);
+    if (dm) {
+      const bool mine = (dm >> lane) & 1u;
+      const double r1 = warp_sum(mine ? ep_ret : 0.0);
+      const double r2 = warp_sum(mine ? ep_ret * ep_ret : 0.0);
+      const int l1 = warp_sum(mine ? ep_len : 0);
+      const unsigned tm = __ballot_sync(0xffffffffu, mine && term);
+      const unsigned um = __ballot_sync(0xffffffffu, mine && trunc && !term);
+      if (lane == 0) {
+        atomicAdd(&p.stats[CL_STAT_EPISODES], (double)__popc(dm));
+        atomicAdd(&p.stats[CL_STAT_RET_SUM], r1);
+        atomicAdd(&p.stats[CL_STAT_RET_SQ], r2);
+        atomicAdd(&p.stats[CL_STAT_LEN_SUM], (double)l1);
+        if (tm) atomicAdd(&p.stats[CL_STAT_TERMINATED], (double)__popc(tm));
+        if (um) atomicAdd(&p.stats[CL_STAT_TRUNCATED], (double)__popc(um));
+      }
+    }
+    if (bm && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)__popc(bm));
+
+    if (live) {
+      const int64_t oo = ROLL ? t * p.obs_ts : 0;
+      if (done) {
+        if (p.term_obs) store_obs<real>(p.term_obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
+        if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;
+        if (p.last_ep_len) p.last_ep_len[i] = ep_len;
+        if (autoreset) {
+          E::reset(s, p, rng, obs);
+          ep_len = 0;
+          ep_ret = 0.0;
+        }
+      }
+      if (p.obs) store_obs<real>(p.obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
+      if (p.reward) {
+        const int64_t ro = (ROLL ? t * p.rew_ts : 0) + i;
+        if (p.reward_f32) ((float*)p.reward)[ro] = (float)rew;
+        else ((real*)p.reward)[ro] = rew;
+      }
+      if (p.done) {
+        p.done[(ROLL ? t * p.done_ts : 0) + i] =
+            (uint8_t)((term ? CL_DONE_TERMINATED : 0) | (trunc ? CL_DONE_TRUNCATED : 0));
+      }
+    }
+  }
+  if (live) {
+    E::store(s, p, i);
+    p.ep_len[i] = ep_len;
+    p.ep_return[i] = ep_ret;
+  }
+}
+
+template <class E>
+__global__ void __launch_bounds__(256) k_reset(const KParams p) {
+  typedef typename E::real real;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  if (p.mask != nullptr && p.mask[i] == 0) return;
+  typename E::S s = {};
+  E::load(s, p, i);  // keeps persistent fields (Adam-dual state, per-env parameters)
+  const Stream rng = make_stream(p, i, p.step_index);
+  real obs[E::OBS];
+  E::reset(s, p, rng, obs);
+  E::store(s, p, i);
+  p.ep_len[i] = 0;
+  p.ep_return[i] = 0.0;
+  if (p.obs) store_obs<real>(p.obs, 0, p.obs_es, p.obs_cs, i, obs, E::OBS, (p.flags & CL_F_OBS_F64) != 0);
+}
+
+template <class E>
+__global__ void __launch_bounds__(256) k_init(const KParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  typename E::S s = {};
+  const Stream rng = make_stream(p, i, 0);
+  E::init_persistent(s, p, rng);
+  E::store(s, p, i);
+  p.ep_len[i] = 0;
+  p.ep_return[i] = 0.0;
+}
+
+template <class E>
+cudaError_t launch_env(const KParams& p, int mode, cudaStream_t st, int block) {
+  const unsigned grid = (unsigned)((p.n + block - 1) / block);
+  switch (mode) {
+    case MODE_STEP: k_step<E, false><<<grid, block, 0, st>>>(p); break;
+    case MODE_ROLLOUT: k_step<E, true><<<grid, block, 0, st>>>(p); break;
+    case MODE_RESET: k_reset<E><<<grid, block, 0, st>>>(p); break;
+    case MODE_INIT: k_init<E><<<grid, block, 0, st>>>(p); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// plane accessors
+template <typename real>
+__device__ __forceinline__ real ldp(const KParams& p, int c, int64_t i) {
+  return ((const real*)p.state)[(int64_t)c * p.n_pad + i];
+}
+template <typename real>
+__device__ __forceinline__ void stp(const KParams& p, int c, int64_t i, real v) {
+  ((real*)p.state)[(int64_t)c * p.n_pad + i] = v;
+}
+
+}  // namespace cl
+
+// per-TU dispatch (implemented in tu_parity.cu / tu_northstar.cu)
+cudaError_t cl_launch_parity(int kind, const cl::KParams& p, int mode, cudaStream_t st, int block);
+cudaError_t cl_launch_northstar(int kind, const cl::KParams& p, int mode, cudaStream_t st, int block);
+cudaError_t cl_occupancy_parity(int kind, int block, int* blocks_per_sm);
+cudaError_t cl_occupancy_northstar(int kind, int block, int* blocks_per_sm);
+cudaError_t cl_fma_peak_launch(int dtype_bytes, int grid, int block, int iters, void* sink, cudaStream_t st);
