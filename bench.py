@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the hot path on B200 (contract: see the task statement).
+
+Workload (BASELINE.json configs[1]): Lorenz targeting env, 65,536 parallel envs per GPU, FP64
+RK4 with S=16 substeps per control interval (the smallest power of two that meets the
+rtol-1e-9 bar against adaptive integration, tests/test_rk4_vs_scipy.py), random actions.
+
+One bench "step" = one rollout chunk: T control intervals for every env, executed by ONE
+launch of the fused rollout kernel (`cl_rollout`).  Inputs: a pre-generated random action
+tensor f32 [T, 3, n_pad] resident in HBM; outputs streamed to HBM every interval: obs f32
+[T, 6, n_pad], reward f64 [T, n_pad], done u8 [T, n_pad].  With T=256 the per-step streams
+(201 MB in, 554 MB out) exceed the 126 MB L2, so no timed iteration finds its inputs cached.
+
+`value`   = all ranks' env-steps / max-over-ranks device time (CUDA events), inputs in HBM.
+`e2e`     = the same env, same metric, driven through the SB3-facing VecEnv API
+            (`step_async(np.ndarray)` / `step_wait()`) with HOST numpy buffers: per control
+            interval an H2D copy of the actions and a D2H copy of obs/reward/done, all inside
+            the timed region.
+`roofline`= the fused rollout kernel against the FP64-FMA peak measured live by a
+            register-resident DFMA chain (MEASURED_PEAKS.json carries no FP64 number), plus
+            its HBM side against MEASURED_PEAKS.json's copy bandwidth.
+`cpu_baseline` / `--impl reference` = the oracle's C restatement (OpenMP, all host cores) on
+            a bounded sample of the same workload; the reference itself is single-env
+            Python (~2.7e4 steps/s/core) and cannot travel to the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+FLOP_PER_SUBSTEP = 87          # Lorenz RK4 substep with 3-channel ZOH control
+BYTES_PER_ENV_STEP = 12 + 24 + 8 + 1   # action f32x3 in; obs f32x6, reward f64, done u8 out
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--chunk", type=int, default=256, help="control intervals per bench step (T)")
+    ap.add_argument("--substeps", type=int, default=16)
+    ap.add_argument("--kind", default="lorenz_rk4")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="bench steps timed on the host-buffer path")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"Lorenz targeting env (RK4 x {args.substeps} substeps, dt=0.01, FP64), "
+                    f"{args.envs_per_gpu} envs/GPU, random actions (BASELINE.json configs[1])",
+        "kind": args.kind, "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
+        "substeps": args.substeps, "control_intervals_per_step": args.chunk,
+        "parallelism": f"env-slab x{world} (no data-path collective; 64 B stats all-reduce per step)",
+        "l2": "per-step action/obs/reward streams (>=750 MB) exceed the 126 MB L2; env state "
+              "(3 MB) lives in registers across the whole launch",
+    }
+
+
+# ---------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """`nvidia-smi -lms` in the background for the duration of the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.th = index, [], None, None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            cols = [c.strip() for c in ln.strip().split(",")]
+            if len(cols) >= 6:
+                self.rows.append(cols)
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+            time.sleep(0.3)   # let the first samples arrive before the timed region starts
+        except Exception:  # noqa: BLE001
+            self.proc = None
+        return self
+
+    def mark(self):
+        return len(self.rows)
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+            self.th.join(timeout=5)
+
+    def summary(self, lo=0, hi=None):
+        rows = self.rows[lo:hi] or self.rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in rows)]
+        mx = float(rows[0][1]) if rows[0][1].replace(".", "").isdigit() else None
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(rows)}
+
+
+# ---------------------------------------------------------------- CPU arms (oracle port)
+def cpu_arm(args, budget_s):
+    """Oracle C port, OpenMP on all host cores, on a bounded sample of the same workload.
+    Returns (env_steps_per_s, cores, sample_text, T_sample, elapsed)."""
+    from oracle import api as O
+    n = args.envs_per_gpu
+    threads = min(O.max_threads(), len(os.sched_getaffinity(0)))
+    O.set_threads(threads)
+    orc = O.Oracle(args.kind, n, flags=O.F_AUTORESET, seed=0, substeps=args.substeps, dt=0.01,
+                   act_limit=1.0, act_gain=50.0, max_episode_steps=1000)
+    orc.reset()
+    t0 = time.perf_counter(); orc.rollout_timed(1); dt1 = time.perf_counter() - t0   # also warms up
+    T = max(1, min(4096, int(budget_s / max(dt1, 1e-6))))
+    t0 = time.perf_counter(); orc.rollout_timed(T); el = time.perf_counter() - t0
+    sample = (f"{n} envs x {T} control intervals ({args.kind}, RK4 x {args.substeps}, synthetic Philox actions), "
+              f"oracle/chaos_oracle.c -O2 OpenMP x{threads}, {el:.2f} s")
+    return n * T / el, threads, sample, T, el
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores."""
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from oracle import api as O
+    n = args.envs_per_gpu
+    threads = min(O.max_threads(), len(os.sched_getaffinity(0)))
+    O.set_threads(threads)
+    orc = O.Oracle(args.kind, n, flags=O.F_AUTORESET, seed=0, substeps=args.substeps, dt=0.01,
+                   act_limit=1.0, act_gain=50.0, max_episode_steps=1000)
+    orc.reset()
+    t0 = time.perf_counter(); orc.rollout_timed(1); dt1 = time.perf_counter() - t0
+    # bounded sample per step: about 0.1 s of CPU work, whole run capped near 2 minutes
+    per_step_budget = min(0.1, 120.0 / max(args.steps + args.warmup, 1))
+    T = max(1, int(per_step_budget / max(dt1, 1e-6)))
+    for _ in range(args.warmup):
+        orc.rollout_timed(T)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.rollout_timed(T)
+    el = time.perf_counter() - t0
+    value = n * T * args.steps / el
+    cfg = workload_config(args, max(world, 1))
+    cfg["reference_sample_intervals_per_step"] = T
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} envs x {T} control intervals per step x {args.steps} steps, "
+                                   f"oracle/chaos_oracle.c (C restatement, OpenMP x{threads}); the reference "
+                                   f"itself is single-env Python and is not present on this box"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- the B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from gym_lorenz_b200 import distributed as D
+    from gym_lorenz_b200.core import ChaosBatch, measure_fma_peak
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+
+    rank, world, local = D.init_process_group()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    slab = D.weak_slab(args.envs_per_gpu, world, rank)
+    N, T, S = slab.num_envs, args.chunk, args.substeps
+
+    batch = ChaosBatch(args.kind, N, device=dev, seed=0, env_id_base=slab.env_id_base, substeps=S,
+                       dt=0.01, autoreset=True, max_episode_steps=1000)
+    batch.reset()
+    NP = batch.n_pad
+    # synthetic random actions, SoA time-major, resident in HBM before the timed region
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    act_soa = torch.rand((T, batch.act_dim, NP), generator=g, device=dev, dtype=torch.float32) * 2 - 1
+    actions = act_soa[:, :, :N].permute(0, 2, 1)       # [T, N, A] view, env stride 1
+    out = {"obs": torch.empty((T, batch.obs_dim, NP), dtype=torch.float32, device=dev),
+           "reward": torch.empty((T, NP), dtype=torch.float64, device=dev),
+           "done": torch.empty((T, NP), dtype=torch.uint8, device=dev)}
+    side = torch.cuda.Stream(device=dev)
+
+    def one_step():
+        batch.rollout(T, actions, out=out)
+        if world > 1:   # episode-statistics all-reduce on a side stream, off the critical path
+            st = batch.stats_tensor(clear=False)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                D.allreduce_stats(st)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    l0 = batch.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        m0 = clk.mark()
+        e0.record()
+        for _ in range(args.steps):
+            one_step()
+        e1.record()
+        barrier()
+        m1 = clk.mark()
+        # kernel-only duration of the dominant kernel (rollout launches back to back, same stream)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(args.steps):
+            batch.rollout(T, actions, out=out)
+        k1.record()
+        torch.cuda.synchronize(dev)
+        m2 = clk.mark()
+    kern_ms = k0.elapsed_time(k1) / args.steps
+    clocks = clk.summary(m0, max(m2, m0 + 1))
+    clocks["samples_in_timed_region"] = m1 - m0
+    ms = e0.elapsed_time(e1)
+    launches = batch.launch_count - l0
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_all = float(tmax.item())
+    env_steps = float(N) * T * args.steps * world
+    value = env_steps / (ms_all * 1e-3)
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+        fp64_peak = measure_fma_peak(local, 8, 0.5)
+        flops = float(N) * T * S * FLOP_PER_SUBSTEP
+        ach = flops / (kern_ms * 1e-3) * 1e-12
+        gbs = float(N) * T * BYTES_PER_ENV_STEP / (kern_ms * 1e-3) * 1e-9
+        roofline = {
+            "kernel": "cl::k_step<EnvLorenzRK4<double>, ROLL=true> (fused T-interval rollout)",
+            "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": ach / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+            "peak_source": "DFMA-chain micro-kernel (cl_measure_fma_peak) run in this process, 2 flop/FMA; "
+                           "MEASURED_PEAKS.json has no FP64 entry",
+            "algorithmic_flop_per_substep": FLOP_PER_SUBSTEP,
+            "fma_issue_ceiling": 87.0 / (2 * 49),
+            "kernel_ms_per_launch": kern_ms,
+            "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": hbm_src},
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_all / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world), "substeps_per_s": value * S,
+            "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
+            "block_size": batch.block_size,
+        }
+
+    # ---- e2e: the SB3-facing VecEnv API with host numpy buffers --------------------------
+    e2e = None
+    if not args.no_e2e:
+        env = BatchedChaosVecEnv(args.kind, N, device=dev, seed=0, env_id_base=slab.env_id_base,
+                                 substeps=S, dt=0.01, max_episode_steps=1000)
+        env.reset()
+        rng = np.random.default_rng(rank)
+        host_actions = [rng.uniform(-1, 1, (N, env.batch.act_dim)).astype(np.float32) for _ in range(8)]
+        chunks = max(1, min(args.e2e_chunks, args.steps))
+        for k in range(32):
+            env.step(host_actions[k % 8])
+        barrier()
+        t0 = time.perf_counter()
+        acc = 0.0
+        for k in range(chunks * T):
+            obs, rew, dones, infos = env.step(host_actions[k % 8])
+            acc += float(rew[0])
+        torch.cuda.synchronize(dev)
+        el = time.perf_counter() - t0
+        tm = torch.tensor([el], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(N) * T * chunks * world / float(tm.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(env.batch.h2d_bytes_per_step * T),
+               "d2h_bytes_per_step": int(env.batch.d2h_bytes_per_step * T),
+               "api": "BatchedChaosVecEnv.step_async(np.ndarray)/step_wait() (SB3 VecEnv contract), "
+                      f"{T} control intervals per bench step, {chunks} bench steps timed, wall clock incl. "
+                      "pinned staging, H2D, kernel, D2H, sync",
+               "us_per_control_interval": float(tm.item()) / (chunks * T) * 1e6}
+        env.close()
+
+    if rank == 0:
+        line["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, sample, _, _ = cpu_arm(args, budget_s=12.0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,7 @@ __device__ __forceinline__ double cube_cr(double x) {
   const double p = x * x;
   const double e = fma(x, x, -p);
   const double r = p * x;
+  if (!isfinite(r)) return r;  // overflow / NaN: same result class as pow(x, 3)
   const double re = fma(p, x, -r);
   return r + fma(e, x, re);
 }

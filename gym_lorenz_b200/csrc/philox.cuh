@@ -13,7 +13,7 @@
 // (dynamic.py:37, lorenz_env_try.py:55-67, lorenz_env_try_pmsm.py:64-65,80); those
 // streams cannot be reproduced by a counter-based generator, so parity tests inject
 // states and noise, and reset is checked distributionally + exactly against
-// oracle/chaos_oracle.c's restatement of this same mapping.
+// the CPU checker's independent restatement of this same mapping.
 #pragma once
 #include <stdint.h>
 

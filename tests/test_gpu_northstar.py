@@ -1,0 +1,125 @@
+"""North-star kinds on the GPU: RK4 x S vs the oracle (1e-12 per interval), vs scipy DOP853
+(1e-9, the tolerance BASELINE.json states), fused rollout == repeated single steps, f32
+variant, per-env parameter randomisation."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def test_lorenz_rk4_per_interval_vs_oracle(oracle_api):
+    import torch
+    O = oracle_api
+    n = 8192
+    for S in (1, 4, 16):
+        b = H.gpu_batch("lorenz_rk4", n, seed=5, substeps=S, autoreset=False, max_episode_steps=0)
+        o = O.Oracle("lorenz_rk4", n, seed=5, substeps=S, dt=0.01, act_limit=1.0, act_gain=50.0)
+        b.reset(); o.reset()
+        assert np.array_equal(b.state.cpu().numpy(), o.state)
+        rng = np.random.default_rng(S)
+        for t in range(4):
+            o.state[...] = b.state.cpu().numpy()  # teacher-forced: same pre-state every interval
+            a = rng.uniform(-1.2, 1.2, (n, 3)).astype(np.float32)
+            obs, rew, done = b.step(torch.as_tensor(a, device=b.device))
+            oo, ro, do, _ = o.step(np.ascontiguousarray(a.T))
+            H.assert_close(b.state.cpu().numpy()[:3], o.state[:3], 1e-12, f"S={S} state", atol=1e-13)
+            H.assert_close(rew.cpu().numpy(), ro, 1e-12, "reward", atol=1e-13)
+            assert np.array_equal(done.cpu().numpy(), do)
+        b.close()
+
+
+def test_lorenz_rk4_vs_scipy_dop853():
+    import torch
+    from scipy.integrate import solve_ivp
+    n = 32
+    b = H.gpu_batch("lorenz_rk4", n, seed=3, substeps=16, autoreset=False, max_episode_steps=0)
+    b.reset()
+    # move onto the attractor first (200 uncontrolled intervals)
+    z = torch.zeros((n, 3), device=b.device)
+    for _ in range(200):
+        b.step(z)
+    st = b.state.cpu().numpy()[:3, :n].T.copy()
+    a = np.random.default_rng(0).uniform(-1, 1, (n, 3)).astype(np.float32)
+    b.step(torch.as_tensor(a, device=b.device))
+    got = b.state.cpu().numpy()[:3, :n].T
+
+    def f(t, s, u):
+        x, y, zz = s
+        return [10 * (y - x) + u[0], x * (28 - zz) - y + u[1], x * y - (8 / 3) * zz + u[2]]
+    worst = 0.0
+    for i in range(n):
+        ref = solve_ivp(f, (0, 0.01), st[i], args=(a[i].astype(np.float64) * 50.0,), method="DOP853",
+                        rtol=1e-13, atol=1e-13).y[:, -1]
+        worst = max(worst, float(np.max(np.abs(got[i] - ref) / np.maximum(np.abs(ref), 1.0))))
+    assert worst < 1e-9, worst
+    b.close()
+
+
+@pytest.mark.parametrize("kind", ["lorenz_rk4", "lorenz3", "hr_sync", "pmsm_sync", "pmsm_rk4"])
+def test_fused_rollout_equals_single_steps_bit_exactly(kind):
+    import torch
+    n, T = 3000, 17
+    kw = dict(seed=11, autoreset=True, max_episode_steps=7)
+    b1 = H.gpu_batch(kind, n, **kw)
+    b2 = H.gpu_batch(kind, n, **kw)
+    b1.reset(); b2.reset()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    amp = 0.05 if kind == "lorenz3" else float(b1.layout.act_high)  # +-500 impulses overflow to NaN
+    acts = (torch.rand((T, n, b1.act_dim), generator=g) * 2 - 1).to(b1.device) * amp
+    out = b1.rollout(T, acts)
+    for t in range(T):
+        obs, rew, done = b2.step(acts[t])
+        assert torch.equal(out["obs"][t, :, :n].t(), obs), (kind, t)
+        assert torch.equal(out["reward"][t, :n], rew)
+        assert torch.equal(out["done"][t, :n], done)
+    assert torch.equal(b1.state, b2.state) and torch.equal(b1.ep_len, b2.ep_len)
+    assert torch.equal(b1.ep_return, b2.ep_return)
+    assert b1.step_index == b2.step_index
+    b1.close(); b2.close()
+
+
+def test_synthetic_action_rollout_vs_oracle(oracle_api):
+    O = oracle_api
+    n, T = 4096, 6
+    b = H.gpu_batch("lorenz_rk4", n, seed=21, substeps=4, env_id_base=77)
+    o = O.Oracle("lorenz_rk4", n, flags=O.F_AUTORESET, seed=21, substeps=4, dt=0.01, act_limit=1.0,
+                 act_gain=50.0, max_episode_steps=1000, env_id_base=77)
+    b.reset(); o.reset()
+    out = b.rollout(T)
+    ref = o.rollout(T, None, synth_amp=1.0)
+    H.assert_close(out["obs"].double().cpu().numpy(), ref["obs"], 1e-6, "obs (f32 store)", atol=1e-6)
+    H.assert_close(out["reward"].cpu().numpy(), ref["reward"], 1e-11, "reward", atol=1e-12)
+    H.assert_close(b.state.cpu().numpy()[:3], o.state[:3], 1e-11, "state", atol=1e-12)
+    b.close()
+
+
+def test_lorenz_rk4_f32_vs_oracle(oracle_api):
+    import torch
+    O = oracle_api
+    n = 4096
+    b = H.gpu_batch("lorenz_rk4_f32", n, seed=5, substeps=8, autoreset=False, max_episode_steps=0)
+    o = O.Oracle("lorenz_rk4_f32", n, seed=5, substeps=8, dt=0.01, act_limit=1.0, act_gain=50.0)
+    b.reset(); o.reset()
+    assert np.array_equal(b.state.cpu().numpy(), o.state)
+    a = np.random.default_rng(0).uniform(-1, 1, (n, 3)).astype(np.float32)
+    b.step(torch.as_tensor(a, device=b.device))
+    o.step(np.ascontiguousarray(a.T))
+    H.assert_close(b.state.cpu().numpy()[:3], o.state[:3], 2e-5, "f32 rk4 state", atol=1e-5)
+    b.close()
+
+
+def test_per_env_parameter_randomisation(oracle_api):
+    O = oracle_api
+    n = 4096
+    b = H.gpu_batch("pmsm_rk4", n, seed=0, param_jitter=0.1)
+    o = O.Oracle("pmsm_rk4", n, seed=0, param_jitter=0.1, substeps=4, dt=0.001, act_gain=50.0)
+    sg = b.state.cpu().numpy()
+    assert np.array_equal(sg[6:8], o.state[6:8])
+    assert 5.46 * 0.9 <= sg[6, :n].min() and sg[6, :n].max() <= 5.46 * 1.1
+    assert 20 * 0.9 <= sg[7, :n].min() and sg[7, :n].max() <= 20 * 1.1
+    assert sg[6, :n].std() > 0.1
+    b.reset()
+    assert np.array_equal(b.state.cpu().numpy()[6:8], sg[6:8])  # parameters survive reset
+    b.close()

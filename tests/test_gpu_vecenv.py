@@ -1,0 +1,164 @@
+"""The SB3 VecEnv contract (stable_baselines3 2.7.1 DummyVecEnv semantics) on the GPU env,
+plus the single-env facades, attribute access used by the reference's scripts, DLPack
+hand-off and checkpoint/resume."""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vecenv_numpy_contract_and_autoreset_infos():
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n = 300
+    hr = BatchedChaosVecEnv("hr_sync", n, seed=1)
+    assert hr.observation_space.shape == (6,) and hr.action_space.shape == (2,)
+    assert hr.observation_space.dtype == np.float32
+    assert float(hr.action_space.low.min()) == -1.0 and float(hr.action_space.high.max()) == 1.0
+    obs = hr.reset()
+    assert obs.shape == (n, 6) and obs.dtype == np.float32
+    assert np.all(np.abs(obs) <= 1.0)  # reset clips both halves (lorenz_env_try.py:73-75)
+    hr.close()
+    env = BatchedChaosVecEnv("lorenz3", n, seed=1, max_episode_steps=5)  # no early termination
+    assert env.num_envs == n and env.action_space.shape == (3,)
+    obs = env.reset()
+    prev = []
+    for t in range(1, 11):
+        a = np.random.default_rng(t).uniform(-0.05, 0.05, (n, 3)).astype(np.float32)
+        env.step_async(a)
+        obs, rew, dones, infos = env.step_wait()
+        prev.append(obs)
+        assert obs.shape == (n, 6) and rew.shape == (n,) and rew.dtype == np.float32
+        assert dones.dtype == np.bool_ and len(infos) == n
+        if t % 5 == 0:
+            assert dones.all()
+            for i in (0, n - 1):
+                assert infos[i]["TimeLimit.truncated"] is True
+                assert infos[i]["terminal_observation"].shape == (6,)
+                assert infos[i]["episode"]["l"] == 5
+                assert np.isfinite(infos[i]["episode"]["r"])
+            assert np.all(np.abs(obs[:, :3]) <= 30.0)   # fresh reset obs (dynamic.py:37)
+        else:
+            assert not dones.any() and all(not d for d in infos)
+    # the zero-copy result ring keeps the previous step's obs intact (SB3 collect_rollouts
+    # reads self._last_obs after the next env.step)
+    snap = prev[-2].copy()
+    assert np.array_equal(prev[-2], snap)
+    st = env.stats()
+    assert st["episodes"] == 2 * n and st["truncated"] == 2 * n
+    env.close()
+
+
+def test_vecenv_get_set_attr_and_env_method(oracle_api):
+    """code/lorenz_pmsm/test_evaluate.py:100-108,123-125 overwrite state1/state2 by attribute,
+    call _get_derivatives and read the states back every step."""
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    env = BatchedChaosVecEnv("pmsm_sync", 4, alpha=0.5)
+    env.reset()
+    env.set_attr("state1", np.array([10.0, -10.0, 15.0], np.float32))
+    env.set_attr("state2", np.array([0.0, 0.0, 0.0], np.float32))
+    assert np.array_equal(env.get_attr("state1")[2], np.array([10.0, -10.0, 15.0], np.float32))
+    d = env.env_method("_get_derivatives", np.array([10.0, -10.0, 15.0], np.float32), [0, 0])[0]
+    # lorenz_env_try_pmsm.py:55-57 in float32
+    x1, x2, x3 = np.float32(10), np.float32(-10), np.float32(15)
+    ref = np.array([-x1 + x2 * x3, -x2 - x1 * x3 + np.float32(20.0) * x3, np.float32(5.46) * (x2 - x3)], np.float32)
+    assert np.array_equal(d, ref)
+    obs, rew, dones, infos = env.step(np.tile(np.array([[-1.0, 1.0]], np.float32), (4, 1)))
+    e = np.asarray(env.get_attr("state1")[0]) - np.asarray(env.get_attr("state2")[0])
+    assert e.tolist() == [9.890000343322754, -9.890000343322754, 14.863499641418457]
+    assert env.get_attr("sigma")[0] == 5.46 and env.get_attr("current_step")[0] == 1
+    assert env.get_attr("render_mode") == [None] * 4
+    assert env.env_is_wrapped(object) == [False] * 4
+    env.close()
+
+
+def test_tensor_path_dlpack_no_host_round_trip():
+    import torch
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    env = BatchedChaosVecEnv("lorenz_rk4", 4096, substeps=4)
+    obs = env.reset_tensor()
+    assert obs.is_cuda and obs.shape == (4096, 6) and obs.dtype == torch.float32
+    cap = env.obs_dlpack()
+    t2 = torch.utils.dlpack.from_dlpack(cap)
+    assert t2.data_ptr() == env.batch.obs_planes.data_ptr()  # zero copy
+    w = torch.randn(6, 3, device=obs.device)
+    for _ in range(3):
+        act = torch.tanh(obs @ w)            # policy consumes the strided view directly
+        obs, rew, done = env.step_tensor(act)
+        assert rew.is_cuda and done.dtype == torch.uint8
+    env.close()
+
+
+def test_single_env_facades_gymnasium_and_old_gym():
+    from gym_lorenz_b200 import envs as E
+    hr = E.HRSyncEnv(add_noise=False)
+    obs, info = hr.reset(seed=3)
+    assert obs.shape == (6,) and obs.dtype == np.float32 and info == {}
+    out = hr.step(np.array([0.3, -0.2], np.float32))
+    assert len(out) == 5 and isinstance(out[1], float) and out[2] is False and out[3] is False
+    hr.state_master = np.array([100.0, 0.0, 0.0]); hr.state_slave = np.zeros(3)
+    obs, r, term, trunc, _ = hr.step(np.zeros(2, np.float32))
+    assert term is True and r == -2000.0          # lorenz_env_try.py:174-176
+    hr.close()
+    pm = E.PMSM_Sync_Env(alpha=0.5)
+    obs, _ = pm.reset(seed=0)
+    assert obs.dtype == np.float32
+    lam0 = pm.lambda_coef
+    pm.step(np.array([1.0, 1.0], np.float32))
+    a1 = pm.adam_step
+    pm.reset()
+    assert pm.adam_step == a1 == 1 and pm.current_step == 0   # Adam state survives reset (:59-75)
+    assert lam0 == 0.0
+    pm.close()
+    lo = E.lorenzEnv_transient()
+    o = lo.reset()
+    assert o.dtype == np.float64 and o.shape == (6,) and lo.t == 0
+    o, r, d, info = lo.step(np.array([600.0, -600.0, 0.0], np.float32))  # clipped to +-500 (dynamic.py:63-65)
+    assert isinstance(d, bool) and info == {}
+    assert lo._get_current()[1] == 0.0
+    pair = E.lorenzEnv_transient.lorenzEnv_transient()
+    o = pair.reset()
+    tgt = np.asarray(pair.state2).copy()
+    pair.step(np.zeros(3, np.float32))
+    assert np.array_equal(np.asarray(pair.state2), tgt)  # target never advanced (dynamic.py:194-219)
+    lo.close(); pair.close()
+
+
+def test_checkpoint_resume_is_bit_exact():
+    import torch
+    n = 2048
+    b = H.gpu_batch("hr_sync", n, seed=4, add_noise=True, max_episode_steps=9)
+    b.reset()
+    a = torch.rand((30, n, 2), device=b.device) * 2 - 1
+    for t in range(10):
+        b.step(a[t])
+    sd = b.state_dict()
+    ref = [tuple(x.clone() for x in b.step(a[t])) for t in range(10, 20)]
+    b2 = H.gpu_batch("hr_sync", n, seed=4, add_noise=True, max_episode_steps=9)
+    b2.load_state_dict(sd)
+    for t in range(10, 20):
+        o, r, d = b2.step(a[t])
+        assert torch.equal(o, ref[t - 10][0]) and torch.equal(r, ref[t - 10][1]) and torch.equal(d, ref[t - 10][2])
+    b.close(); b2.close()
+
+
+def test_reset_distribution_and_mask():
+    import torch
+    n = 100000
+    b = H.gpu_batch("lorenz3", n, seed=123)
+    b.reset()
+    s = b.state.cpu().numpy()[:3, :n]
+    assert s.min() >= -30 and s.max() < 30
+    assert abs(s.mean()) < 0.2 and abs(s.std() - 60 / np.sqrt(12)) < 0.1
+    # Kolmogorov-Smirnov against U(-30,30)
+    from scipy import stats
+    assert stats.kstest(s[0], "uniform", args=(-30, 60)).pvalue > 1e-3
+    assert abs(np.corrcoef(s[0], s[1])[0, 1]) < 0.02
+    before = b.state.clone()
+    mask = torch.zeros(n, dtype=torch.uint8, device=b.device); mask[::2] = 1
+    b.reset(mask)
+    after = b.state
+    assert torch.equal(after[:, 1:n:2], before[:, 1:n:2])
+    assert not torch.equal(after[:3, 0:n:2], before[:3, 0:n:2])
+    b.close()
