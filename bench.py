@@ -235,6 +235,7 @@ def run_b200(args):
             one_step()
         e1.record()
         barrier()
+        l1 = batch.launch_count
         m1 = clk.mark()
         # kernel-only duration of the dominant kernel (rollout launches back to back, same stream)
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -248,7 +249,7 @@ def run_b200(args):
     clocks = clk.summary(m0, max(m2, m0 + 1))
     clocks["samples_in_timed_region"] = m1 - m0
     ms = e0.elapsed_time(e1)
-    launches = batch.launch_count - l0
+    launches = l1 - l0
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

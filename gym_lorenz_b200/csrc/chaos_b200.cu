@@ -144,6 +144,10 @@ extern "C" int cl_create(const cl_config* cfg, cl_ctx** out) {
   ctx->lay = kLayouts[cfg->kind];
   ctx->sm_count = prop.multiProcessorCount;
   ctx->block = pick_block(cfg->num_envs, ctx->sm_count);
+  if (const char* ov = getenv("CHAOS_B200_BLOCK")) {  // tuning override: 32..256, multiple of 32
+    const int b = atoi(ov);
+    if (b >= 32 && b <= 256 && (b % 32) == 0) ctx->block = b;
+  }
   ctx->step_index = 0;
   e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { int r = fail(nullptr, CL_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); free(ctx); return r; }
@@ -211,6 +215,14 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
   p.state = buf->state; p.aux_int = buf->aux_int; p.ep_len = buf->ep_len;
   p.ep_return = buf->ep_return; p.stats = buf->stats;
   p.bc1 = ctx->d_bc1; p.bc2 = ctx->d_bc2; p.bc1_n = ctx->bc1_n; p.bc2_n = ctx->bc2_n;
+  if (!is_parity(c.kind)) {
+    // same IEEE operations the kernel used to do per thread, done once here
+    p.h = c.dt / (double)c.substeps; p.hh = 0.5 * p.h; p.h3 = p.h / 3.0; p.h6 = p.h / 6.0;
+    p.hf = (float)p.h; p.hhf = 0.5f * p.hf; p.h3f = p.hf / 3.0f; p.h6f = p.hf / 6.0f;
+    if (c.kind == CL_ENV_PMSM_RK4) { p.nom[0] = 5.46; p.nom[1] = 20.0; p.nom[2] = 0.0; }
+    else { p.nom[0] = 10.0; p.nom[1] = 28.0; p.nom[2] = 8.0 / 3.0; }
+    for (int k = 0; k < 3; ++k) p.nomf[k] = (float)p.nom[k];
+  }
   if (io) {
     p.action = io->action; p.act_es = io->act_es; p.act_cs = io->act_cs;
     p.noise = io->noise;

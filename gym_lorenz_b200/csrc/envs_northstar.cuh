@@ -24,10 +24,14 @@ __device__ __forceinline__ void lorenz_rhs_u(const LorenzPar<R>& q, R x, R y, R 
   dz = fma(x, y, fma(-q.beta, z, u3));
 }
 
+// Step sizes (h, h/2, h/3, h/6) and -- on the warp-uniform fast path -- the parameters arrive
+// as kernel-parameter (constant-bank) operands: on sm_100 a DFMA with three distinct register
+// sources issues every 3 cycles per scheduler, one with <= 2 register sources every 2
+// (tools/dfma_probe.cu, DESIGN.md "FP64 cost model"), so only the 8 inherently three-register
+// FMAs per substep (dy, dz of each stage) pay the slow rate.
 template <typename R>
 __device__ __forceinline__ void lorenz_rk4(const LorenzPar<R>& q, R& x, R& y, R& z, R u1, R u2, R u3,
-                                           R h, int substeps) {
-  const R hh = R(0.5) * h, h6 = h / R(6), h3 = h / R(3);
+                                           const R h, const R hh, const R h3, const R h6, int substeps) {
 #pragma unroll 2
   for (int k = 0; k < substeps; ++k) {
     R k1x, k1y, k1z, kx, ky, kz, ax, ay, az;
@@ -47,10 +51,18 @@ template <typename R>
 struct EnvLorenzRK4 {
   typedef R real;
   enum { NSTATE = 6, NINT = 0, OBS = 6, ACT = 3, NOISE = 0 };
-  struct S { R x, y, z; LorenzPar<R> q; };
+  struct S { R x, y, z; LorenzPar<R> q; bool uni; };
   __device__ static void load(S& s, const KParams& p, int64_t i) {
     s.x = ldp<R>(p, 0, i); s.y = ldp<R>(p, 1, i); s.z = ldp<R>(p, 2, i);
     s.q.sigma = ldp<R>(p, 3, i); s.q.rho = ldp<R>(p, 4, i); s.q.beta = ldp<R>(p, 5, i);
+  }
+  // all 32 lanes vote: if every live env of the warp carries the nominal parameters, the warp
+  // integrates with them as constant-bank operands; otherwise with its per-env registers.
+  __device__ static void prepare(S& s, const KParams& p, bool live) {
+    const bool same = !live || (sizeof(R) == 8
+        ? (s.q.sigma == (R)p.nom[0] && s.q.rho == (R)p.nom[1] && s.q.beta == (R)p.nom[2])
+        : (s.q.sigma == (R)p.nomf[0] && s.q.rho == (R)p.nomf[1] && s.q.beta == (R)p.nomf[2]));
+    s.uni = __all_sync(0xffffffffu, same);
   }
   __device__ static void store(const S& s, const KParams& p, int64_t i) {
     stp<R>(p, 0, i, s.x); stp<R>(p, 1, i, s.y); stp<R>(p, 2, i, s.z);
@@ -85,8 +97,21 @@ struct EnvLorenzRK4 {
     const R u1 = (R)clipf(a[0], -lim, lim) * g;
     const R u2 = (R)clipf(a[1], -lim, lim) * g;
     const R u3 = (R)clipf(a[2], -lim, lim) * g;
-    const R h = (R)(p.dt / (double)p.substeps);
-    lorenz_rk4<R>(s.q, s.x, s.y, s.z, u1, u2, u3, h, p.substeps);
+    if (sizeof(R) == 8) {
+      if (s.uni) {
+        const LorenzPar<R> qc = {(R)p.nom[0], (R)p.nom[1], (R)p.nom[2]};
+        lorenz_rk4<R>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6, p.substeps);
+      } else {
+        lorenz_rk4<R>(s.q, s.x, s.y, s.z, u1, u2, u3, (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6, p.substeps);
+      }
+    } else {
+      if (s.uni) {
+        const LorenzPar<R> qc = {(R)p.nomf[0], (R)p.nomf[1], (R)p.nomf[2]};
+        lorenz_rk4<R>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f, p.substeps);
+      } else {
+        lorenz_rk4<R>(s.q, s.x, s.y, s.z, u1, u2, u3, (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f, p.substeps);
+      }
+    }
     observe(s, obs);
     const R e = fabs(s.x) + fabs(s.y) + fabs(s.z);
     rew = -e;                      // dynamic.py:84
@@ -107,9 +132,8 @@ __device__ __forceinline__ void pmsm_rhs_u(const PMSMPar& q, const double* x, do
   d[2] = q.sigma * (x[1] - x[2]);
 }
 
-__device__ __forceinline__ void pmsm_rk4(const PMSMPar& q, double* x, double u1, double u2, double h,
-                                         int substeps) {
-  const double hh = 0.5 * h, h6 = h / 6.0, h3 = h / 3.0;
+__device__ __forceinline__ void pmsm_rk4(const PMSMPar& q, double* x, double u1, double u2, const double h,
+                                         const double hh, const double h3, const double h6, int substeps) {
 #pragma unroll 2
   for (int k = 0; k < substeps; ++k) {
     double k1[3], k2[3], w[3], acc[3];
@@ -131,11 +155,15 @@ __device__ __forceinline__ void pmsm_rk4(const PMSMPar& q, double* x, double u1,
 struct EnvPMSMRK4 {
   typedef double real;
   enum { NSTATE = 8, NINT = 0, OBS = 6, ACT = 2, NOISE = 0 };
-  struct S { double a[3], b[3]; PMSMPar q; };
+  struct S { double a[3], b[3]; PMSMPar q; bool uni; };
   __device__ static void load(S& s, const KParams& p, int64_t i) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) { s.a[c] = ldp<double>(p, c, i); s.b[c] = ldp<double>(p, 3 + c, i); }
     s.q.sigma = ldp<double>(p, 6, i); s.q.gamma = ldp<double>(p, 7, i);
+  }
+  __device__ static void prepare(S& s, const KParams& p, bool live) {
+    const bool same = !live || (s.q.sigma == p.nom[0] && s.q.gamma == p.nom[1]);
+    s.uni = __all_sync(0xffffffffu, same);
   }
   __device__ static void store(const S& s, const KParams& p, int64_t i) {
 #pragma unroll
@@ -176,9 +204,14 @@ struct EnvPMSMRK4 {
     const float lim = (float)p.act_limit;
     const double u1 = (double)clipf(a[0], -lim, lim) * p.act_gain;
     const double u2 = (double)clipf(a[1], -lim, lim) * p.act_gain;
-    const double h = p.dt / (double)p.substeps;
-    pmsm_rk4(s.q, s.a, 0.0, 0.0, h, p.substeps);
-    pmsm_rk4(s.q, s.b, u1, u2, h, p.substeps);
+    if (s.uni) {
+      const PMSMPar qc = {p.nom[0], p.nom[1]};
+      pmsm_rk4(qc, s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
+      pmsm_rk4(qc, s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
+    } else {
+      pmsm_rk4(s.q, s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
+      pmsm_rk4(s.q, s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
+    }
     observe(s, obs);
     const double e0 = fabs(obs[0]), e1 = fabs(obs[1]), e2 = fabs(obs[2]);
     const double E = e0 + e1 + e2;

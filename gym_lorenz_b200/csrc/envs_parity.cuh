@@ -103,6 +103,7 @@ struct EnvLorenz3 {
   __device__ static bool time_limit(const KParams& p, int32_t n) {
     return p.max_steps > 0 && n >= p.max_steps;
   }
+  __device__ static void prepare(S&, const KParams&, bool) {}
   __device__ static void init_persistent(S&, const KParams&, const Stream&) {}
   __device__ static void observe(const S& s, double* obs) {
     obs[0] = s.x; obs[1] = s.y; obs[2] = s.z;
@@ -158,6 +159,7 @@ struct EnvLorenz3Pair {
   __device__ static bool time_limit(const KParams& p, int32_t n) {
     return p.max_steps > 0 && n >= p.max_steps;
   }
+  __device__ static void prepare(S&, const KParams&, bool) {}
   __device__ static void init_persistent(S&, const KParams&, const Stream&) {}
   __device__ static void observe(const S& s, double* obs) {
     double o[6];
@@ -217,6 +219,7 @@ struct EnvLorenz4Pair {
   __device__ static bool time_limit(const KParams& p, int32_t n) {
     return p.max_steps > 0 && n >= p.max_steps;
   }
+  __device__ static void prepare(S&, const KParams&, bool) {}
   __device__ static void init_persistent(S&, const KParams&, const Stream&) {}
   __device__ static void observe(const S& s, double* obs) {
     double da[4], db[4];
@@ -279,6 +282,7 @@ struct EnvHRSync {
   __device__ static bool time_limit(const KParams& p, int32_t n) {
     return p.max_steps > 0 && n >= p.max_steps;
   }
+  __device__ static void prepare(S&, const KParams&, bool) {}
   __device__ static void init_persistent(S&, const KParams&, const Stream&) {}
   // lorenz_env_try.py:49-78
   __device__ static void reset(S& s, const KParams& p, const Stream& rng, double* obs) {
@@ -371,6 +375,7 @@ struct EnvPMSMSync {
   __device__ static bool time_limit(const KParams& p, int32_t n) {
     return n >= 2000 || (p.max_steps > 0 && n >= p.max_steps);
   }
+  __device__ static void prepare(S&, const KParams&, bool) {}
   __device__ static void init_persistent(S& s, const KParams&, const Stream&) {
     s.lam = 0.0f; s.m = 0.0f; s.v = 0.0f; s.adam = 0;  // :16,25-27
   }
@@ -478,6 +483,7 @@ struct EnvPMSMClassic {
   __device__ static bool time_limit(const KParams& p, int32_t n) {
     return p.max_steps > 0 && n >= p.max_steps;
   }
+  __device__ static void prepare(S&, const KParams&, bool) {}
   __device__ static void init_persistent(S&, const KParams&, const Stream&) {}
   __device__ static void observe(const S& s, double* obs) {
     double da[3], db[3];
@@ -540,6 +546,7 @@ struct EnvPMSMSingle {
   __device__ static bool time_limit(const KParams& p, int32_t n) {
     return p.max_steps > 0 && n >= p.max_steps;
   }
+  __device__ static void prepare(S&, const KParams&, bool) {}
   __device__ static void init_persistent(S&, const KParams&, const Stream&) {}
   __device__ static void observe(const S& s, double* obs) {
     obs[0] = s.x; obs[1] = s.y; obs[2] = s.z;

@@ -47,6 +47,14 @@ struct KParams {
   const float* bc1;
   const float* bc2;
   int32_t bc1_n, bc2_n;
+  // RK4 kinds: step sizes precomputed on the host so they are constant-bank operands of the
+  // FMAs (a DFMA with three distinct REGISTER sources issues at 2/3 rate on sm_100, see
+  // DESIGN.md "FP64 cost model"): h = dt/S, hh = h/2, h3 = h/3, h6 = h/6 (+ float copies),
+  // and the nominal parameters for the warp-uniform fast path.
+  double h, hh, h3, h6;
+  float hf, hhf, h3f, h6f;
+  double nom[3];
+  float nomf[3];
 };
 
 enum LaunchMode { MODE_STEP = 0, MODE_ROLLOUT = 1, MODE_RESET = 2, MODE_INIT = 3 };
@@ -137,10 +145,18 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
     ep_len = p.ep_len[i];
     ep_ret = p.ep_return[i];
   }
+  E::prepare(s, p, live);  // executed by all 32 lanes (may vote)
   const bool obs64 = (p.flags & CL_F_OBS_F64) != 0;
   const bool autoreset = (p.flags & CL_F_AUTORESET) != 0;
   const bool want_noise = E::NOISE > 0 && E::uses_noise(p);
   const int T = ROLL ? p.T : 1;
+
+  // actions are fetched one control interval ahead so that their HBM latency hides behind
+  // the previous interval's integration (only ~3.5 warps per scheduler at 65,536 envs)
+  float a_next[E::ACT];
+#pragma unroll
+  for (int c = 0; c < E::ACT; ++c)
+    a_next[c] = (live && p.action != nullptr) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
 
   for (int t = 0; t < T; ++t) {
     const uint64_t step = p.step_index + (uint64_t)t;
@@ -154,8 +170,12 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
       for (int c = 0; c < E::ACT; ++c) a[c] = p.synth_amp * (2.0f * u01_24(w[c & 3]) - 1.0f);
     } else {
 #pragma unroll
-      for (int c = 0; c < E::ACT; ++c)
-        a[c] = live ? p.action[(ROLL ? t * p.act_ts : 0) + i * p.act_es + c * p.act_cs] : 0.0f;
+      for (int c = 0; c < E::ACT; ++c) a[c] = a_next[c];
+      if (ROLL && live && t + 1 < T) {
+#pragma unroll
+        for (int c = 0; c < E::ACT; ++c)
+          a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
+      }
     }
 
     double nz[E::NOISE > 0 ? E::NOISE : 1];
