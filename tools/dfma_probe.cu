@@ -38,6 +38,25 @@ __global__ void __launch_bounds__(1024) k_op(int iters, const double* in, double
   if (s == -1.2345) out[0] = s;
 }
 
+// half-warp test: only `active` lanes of each warp execute the chain
+__global__ void __launch_bounds__(1024) k_half(int iters, int active, const double* in, double* out) {
+  if ((threadIdx.x & 31) >= active) return;
+  double a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = in[threadIdx.x + j];
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fma(a[j], 0.9999999, 1e-9);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == -1.2345) out[0] = s;
+}
+
 // ---------------- RK4 variants ------------------------------------------------------------
 struct Par { double sigma, rho, beta; };
 __device__ __forceinline__ void rhs(const Par& q, double x, double y, double z, double u1, double u2, double u3,
@@ -166,6 +185,13 @@ int main() {
     }
   }
 
+  printf("\n== 1b. DFMA r,c,c with only the first `active` lanes of each warp executing (4 warps/SMSP) ==\n");
+  for (int active : {32, 24, 16, 8, 1}) {
+    auto L = [&]() { k_half<<<sms, 512>>>(iters, active, in, out); };
+    float ms = time_ms(L, 5);
+    printf("active lanes=%2d  %8.3f ms  %.2f cyc/warp-instr\n", active, ms, ms * 1e-3 * 1.965e9 / ((double)iters * 64.0 * 4));
+  }
+  if (getenv("PROBE_SHORT")) return 0;
   printf("\n== 2. Lorenz RK4 loop variants, N=65536, S=16, T=64 (4096 substeps/env... x) ==\n");
   Args a; a.dt = 0.01; a.S = 16; a.h = a.dt / 16; a.hh = 0.5 * a.h; a.h3 = a.h / 3; a.h6 = a.h / 6;
   a.sigma = 10; a.rho = 28; a.beta = 8.0 / 3.0;
