@@ -113,6 +113,7 @@ SYMBOLS = [
     ("cl_measure_fma_peak", C.c_int, [C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_double)]),
     ("cl_launch_count", C.c_int64, [_VP]),
     ("cl_block_size", C.c_int, [_VP]),
+    ("cl_dyn_launch_count", C.c_int64, [_VP]),
     ("cl_philox4x32_10", None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("cl_uniform53", C.c_double, [C.c_uint32, C.c_uint32, C.c_double, C.c_double]),
 ]

@@ -121,6 +121,10 @@ class ChaosBatch:
         return self.lib.cl_block_size(self.ctx)
 
     @property
+    def dyn_launch_count(self) -> int:
+        return self.lib.cl_dyn_launch_count(self.ctx)
+
+    @property
     def launch_count(self) -> int:
         return self.lib.cl_launch_count(self.ctx)
 

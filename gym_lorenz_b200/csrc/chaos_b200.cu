@@ -29,6 +29,7 @@ const cl_layout kLayouts[CL_ENV_KIND_COUNT] = {
     /* PMSM_RK4      */ {8, 8, 0, 6, 2, 0, -1.0, 1.0, -HUGE_VAL, HUGE_VAL, 2000, 0},
 };
 
+const int CL_DYN_CHUNK_DEFAULT = 8;
 const int kHostRing = 3;  // pinned output slots: obs returned at step t stays valid through t+2
 
 struct HostSlot {
@@ -70,6 +71,9 @@ struct cl_ctx {
   float* d_bc2;
   int bc1_n, bc2_n;
   HostStage hs;
+  uint32_t* d_dyn;      // [1 + n_envwarps]: task counter + per-env-warp progress (k_rollout_dyn)
+  int dyn_bps;          // resident worker blocks per SM (0 = not yet queried)
+  int64_t dyn_launches;
 };
 
 static char g_err[512] = "";
@@ -196,6 +200,7 @@ extern "C" int cl_destroy(cl_ctx* ctx) {
   host_stage_free(ctx);
   if (ctx->d_bc1) cudaFree(ctx->d_bc1);
   if (ctx->d_bc2) cudaFree(ctx->d_bc2);
+  if (ctx->d_dyn) cudaFree(ctx->d_dyn);
   free(ctx);
   return CL_OK;
 }
@@ -222,6 +227,7 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
     if (c.kind == CL_ENV_PMSM_RK4) { p.nom[0] = 5.46; p.nom[1] = 20.0; p.nom[2] = 0.0; }
     else { p.nom[0] = 10.0; p.nom[1] = 28.0; p.nom[2] = 8.0 / 3.0; }
     for (int k = 0; k < 3; ++k) p.nomf[k] = (float)p.nom[k];
+    p.act_limit_f = (float)c.act_limit; p.act_gain_f = (float)c.act_gain;
   }
   if (io) {
     p.action = io->action; p.act_es = io->act_es; p.act_cs = io->act_cs;
@@ -275,6 +281,19 @@ extern "C" int cl_step(cl_ctx* ctx, void* stream, const cl_buffers* buf, const c
   return r;
 }
 
+// Dynamic (env-warp x interval-chunk) scheduling pays off when the env-warps do not divide
+// evenly over the 4 x SMs warp schedulers; CHAOS_B200_DYN=0/1 forces it off/on.
+static bool want_dynamic(const cl_ctx* ctx, int T, int chunk) {
+  const char* ov = getenv("CHAOS_B200_DYN");
+  if (ov && ov[0] == '0') return false;
+  const int64_t W = (ctx->cfg.num_envs + 31) / 32, nsched = (int64_t)ctx->sm_count * 4;
+  if (T < 2 * chunk) return false;
+  if (ov && ov[0] == '1') return true;
+  if (W <= nsched) return false;
+  const double eff = (double)W / (double)(((W + nsched - 1) / nsched) * nsched);
+  return eff < 0.95;
+}
+
 extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, const cl_io* io,
                           const cl_rollout_desc* d) {
   if (!ctx) return fail(nullptr, CL_EINVAL, "null ctx");
@@ -285,11 +304,51 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
   if (r) return r;
   p.T = d->T; p.act_ts = d->act_ts; p.obs_ts = d->obs_ts; p.rew_ts = d->rew_ts; p.done_ts = d->done_ts;
   p.synth_amp = (float)d->synth_amp;
+  cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(ctx->cfg.device));
-  r = launch(ctx, p, cl::MODE_ROLLOUT, (cudaStream_t)stream);
+  int chunk = CL_DYN_CHUNK_DEFAULT;
+  if (const char* ov = getenv("CHAOS_B200_DYN_CHUNK")) { const int c = atoi(ov); if (c >= 1 && c <= 32) chunk = c; }
+  int mode = cl::MODE_ROLLOUT;
+  if (want_dynamic(ctx, d->T, chunk)) {
+    const int64_t W = (ctx->cfg.num_envs + 31) / 32;
+    if (!ctx->d_dyn) CU(cudaMalloc((void**)&ctx->d_dyn, sizeof(uint32_t) * (size_t)(W + 1)));
+    if (!ctx->dyn_bps) {
+      int occ = 0;
+      cudaError_t e = is_parity(ctx->cfg.kind) ? cl_dyn_occupancy_parity(ctx->cfg.kind, chunk, &occ)
+                                               : cl_dyn_occupancy_northstar(ctx->cfg.kind, chunk, &occ);
+      if (e != cudaSuccess) return fail(ctx, CL_ECUDA, "dyn occupancy query: %s", cudaGetErrorString(e));
+      // keep the worker count below the env-warp count (see k_rollout_dyn: no dependency waits)
+      int bps = (int)(W / ((int64_t)ctx->sm_count * 4));
+      bps = bps < 1 ? 1 : (bps > 4 ? 4 : bps);
+      if (const char* ov = getenv("CHAOS_B200_DYN_BPS")) { const int b = atoi(ov); if (b >= 1 && b <= 16) bps = b; }
+      ctx->dyn_bps = occ < bps ? occ : bps;
+    }
+    if (ctx->dyn_bps >= 1) {
+      CU(cudaMemsetAsync(ctx->d_dyn, 0, sizeof(uint32_t) * (size_t)(W + 1), st));
+      p.dyn_counter = ctx->d_dyn;
+      p.dyn_progress = ctx->d_dyn + 1;
+      p.dyn_chunk = chunk;
+      p.dyn_nchunks = (d->T + chunk - 1) / chunk;
+      p.dyn_nwarps = (int32_t)W;
+      // every SM gets its full set of resident worker blocks: only W tasks can run at any time
+      // (one per env-warp), the surplus workers wait -- what matters is that each of the 592
+      // warp schedulers always has at least one or two runnable workers
+      const int64_t workers = (int64_t)ctx->sm_count * ctx->dyn_bps;
+      const int64_t tasks = W * (int64_t)((d->T + chunk - 1) / chunk);
+      p.dyn_grid = (int32_t)(workers * 4 < tasks ? workers : (tasks + 3) / 4);
+      // bulk-copy staging needs unit env stride, 16 B alignment and whole 128 B rows in bounds
+      p.dyn_tma = (io->action != nullptr && io->act_es == 1 && (io->act_cs % 4) == 0 && (d->act_ts % 4) == 0 &&
+                   ((uintptr_t)io->action % 16) == 0 && io->act_cs >= W * 32) ? 1 : 0;
+      mode = cl::MODE_ROLLOUT_DYN;
+      ctx->dyn_launches += 1;
+    }
+  }
+  r = launch(ctx, p, mode, st);
   if (r == CL_OK) ctx->step_index += (uint64_t)d->T;
   return r;
 }
+
+extern "C" int64_t cl_dyn_launch_count(const cl_ctx* ctx) { return ctx ? ctx->dyn_launches : 0; }
 
 extern "C" int cl_derivatives(cl_ctx* ctx, void* stream, const void* state, const float* action,
                               void* out, int64_t n) {

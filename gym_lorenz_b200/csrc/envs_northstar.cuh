@@ -46,6 +46,38 @@ __device__ __forceinline__ void lorenz_rk4(const LorenzPar<R>& q, R& x, R& y, R&
   }
 }
 
+// Fully unrolled variant for the common substep counts: without an inner loop ptxas does not
+// force the warp to drain its outstanding loads (the next interval's action prefetch) at a loop
+// head, so that latency hides behind the S x 49 FMA-pipe instructions of the interval.
+template <typename R, int S>
+__device__ __forceinline__ void lorenz_rk4_fixed(const LorenzPar<R>& q, R& x, R& y, R& z, R u1, R u2, R u3,
+                                                 const R h, const R hh, const R h3, const R h6) {
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    R k1x, k1y, k1z, kx, ky, kz, ax, ay, az;
+    lorenz_rhs_u(q, x, y, z, u1, u2, u3, k1x, k1y, k1z);
+    ax = fma(h6, k1x, x); ay = fma(h6, k1y, y); az = fma(h6, k1z, z);
+    lorenz_rhs_u(q, fma(hh, k1x, x), fma(hh, k1y, y), fma(hh, k1z, z), u1, u2, u3, kx, ky, kz);
+    ax = fma(h3, kx, ax); ay = fma(h3, ky, ay); az = fma(h3, kz, az);
+    lorenz_rhs_u(q, fma(hh, kx, x), fma(hh, ky, y), fma(hh, kz, z), u1, u2, u3, k1x, k1y, k1z);
+    ax = fma(h3, k1x, ax); ay = fma(h3, k1y, ay); az = fma(h3, k1z, az);
+    lorenz_rhs_u(q, fma(h, k1x, x), fma(h, k1y, y), fma(h, k1z, z), u1, u2, u3, kx, ky, kz);
+    x = fma(h6, kx, ax); y = fma(h6, ky, ay); z = fma(h6, kz, az);
+  }
+}
+
+template <typename R>
+__device__ __forceinline__ void lorenz_rk4_any(const LorenzPar<R>& q, R& x, R& y, R& z, R u1, R u2, R u3,
+                                               const R h, const R hh, const R h3, const R h6, int S) {
+  switch (S) {  // warp-uniform
+    case 16: lorenz_rk4_fixed<R, 16>(q, x, y, z, u1, u2, u3, h, hh, h3, h6); break;
+    case 8: lorenz_rk4_fixed<R, 8>(q, x, y, z, u1, u2, u3, h, hh, h3, h6); break;
+    case 4: lorenz_rk4_fixed<R, 4>(q, x, y, z, u1, u2, u3, h, hh, h3, h6); break;
+    case 1: lorenz_rk4_fixed<R, 1>(q, x, y, z, u1, u2, u3, h, hh, h3, h6); break;
+    default: lorenz_rk4<R>(q, x, y, z, u1, u2, u3, h, hh, h3, h6, S); break;
+  }
+}
+
 // CL_ENV_LORENZ_RK4 / _F32.  planes: x y z sigma rho beta
 template <typename R>
 struct EnvLorenzRK4 {
@@ -92,22 +124,22 @@ struct EnvLorenzRK4 {
   }
   __device__ static void step(S& s, const KParams& p, const float* a, const double*, R* obs, R& rew,
                               bool& term) {
-    const float lim = (float)p.act_limit;
-    const R g = (R)p.act_gain;
+    const float lim = p.act_limit_f;
+    const R g = sizeof(R) == 8 ? (R)p.act_gain : (R)p.act_gain_f;
     const R u1 = (R)clipf(a[0], -lim, lim) * g;
     const R u2 = (R)clipf(a[1], -lim, lim) * g;
     const R u3 = (R)clipf(a[2], -lim, lim) * g;
     if (sizeof(R) == 8) {
       if (s.uni) {
         const LorenzPar<R> qc = {(R)p.nom[0], (R)p.nom[1], (R)p.nom[2]};
-        lorenz_rk4<R>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6, p.substeps);
+        lorenz_rk4_any<R>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6, p.substeps);
       } else {
         lorenz_rk4<R>(s.q, s.x, s.y, s.z, u1, u2, u3, (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6, p.substeps);
       }
     } else {
       if (s.uni) {
         const LorenzPar<R> qc = {(R)p.nomf[0], (R)p.nomf[1], (R)p.nomf[2]};
-        lorenz_rk4<R>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f, p.substeps);
+        lorenz_rk4_any<R>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f, p.substeps);
       } else {
         lorenz_rk4<R>(s.q, s.x, s.y, s.z, u1, u2, u3, (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f, p.substeps);
       }

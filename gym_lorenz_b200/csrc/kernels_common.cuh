@@ -55,9 +55,14 @@ struct KParams {
   float hf, hhf, h3f, h6f;
   double nom[3];
   float nomf[3];
+  float act_limit_f, act_gain_f;
+  // dynamic rollout scheduling (k_rollout_dyn)
+  uint32_t* dyn_counter;
+  uint32_t* dyn_progress;
+  int32_t dyn_chunk, dyn_nchunks, dyn_nwarps, dyn_tma, dyn_grid;
 };
 
-enum LaunchMode { MODE_STEP = 0, MODE_ROLLOUT = 1, MODE_RESET = 2, MODE_INIT = 3 };
+enum LaunchMode { MODE_STEP = 0, MODE_ROLLOUT = 1, MODE_RESET = 2, MODE_INIT = 3, MODE_ROLLOUT_DYN = 4 };
 
 // ---- small numeric helpers -----------------------------------------------------------
 
@@ -128,11 +133,94 @@ __device__ __forceinline__ void store_obs(void* base, int64_t off, int64_t es, i
   }
 }
 
-// ---- the step / rollout kernel ---------------------------------------------------------
+// ---- one control interval of one env (shared by the static and the dynamic kernels) ----
+
+template <class E, bool ROLL>
+__device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, double& ep_ret,
+                                             const KParams& p, const int64_t i, const bool live,
+                                             const unsigned lane, const int t, const Stream& rng,
+                                             const float* a, const bool want_noise, const bool obs64,
+                                             const bool autoreset) {
+  typedef typename E::real real;
+  double nz[E::NOISE > 0 ? E::NOISE : 1];
+  nz[0] = 0.0;
+  if (want_noise) {
+    if (p.noise != nullptr) {
+#pragma unroll
+      for (int c = 0; c < E::NOISE; ++c) nz[c] = live ? p.noise[c * p.n_pad + i] : 0.0;
+    } else {
+      draw_normal<(E::NOISE > 0 ? E::NOISE : 1)>(rng, TAG_NOISE, nz);
+    }
+  }
+
+  real obs[E::OBS];
+  real rew;
+  bool term;
+  E::step(s, p, a, nz, obs, rew, term);
+  ep_len += 1;
+  ep_ret += (double)rew;
+  const bool trunc = E::time_limit(p, ep_len);
+  const bool done = term || trunc;
+  const bool bad = !E::finite(s);
+
+  // warp-aggregated statistics (one set of atomics per warp, only when something ended)
+  const unsigned dm = __ballot_sync(0xffffffffu, live && done && autoreset);
+  const unsigned bm = __ballot_sync(0xffffffffu, live && bad);
+  if (dm) {
+    const bool mine = (dm >> lane) & 1u;
+    const double r1 = warp_sum(mine ? ep_ret : 0.0);
+    const double r2 = warp_sum(mine ? ep_ret * ep_ret : 0.0);
+    const int l1 = warp_sum(mine ? ep_len : 0);
+    const unsigned tm = __ballot_sync(0xffffffffu, mine && term);
+    const unsigned um = __ballot_sync(0xffffffffu, mine && trunc && !term);
+    if (lane == 0) {
+      atomicAdd(&p.stats[CL_STAT_EPISODES], (double)__popc(dm));
+      atomicAdd(&p.stats[CL_STAT_RET_SUM], r1);
+      atomicAdd(&p.stats[CL_STAT_RET_SQ], r2);
+      atomicAdd(&p.stats[CL_STAT_LEN_SUM], (double)l1);
+      if (tm) atomicAdd(&p.stats[CL_STAT_TERMINATED], (double)__popc(tm));
+      if (um) atomicAdd(&p.stats[CL_STAT_TRUNCATED], (double)__popc(um));
+    }
+  }
+  if (bm && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)__popc(bm));
+
+  if (live) {
+    const int64_t oo = ROLL ? t * p.obs_ts : 0;
+    if (done) {
+      if (p.term_obs) store_obs<real>(p.term_obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
+      if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;
+      if (p.last_ep_len) p.last_ep_len[i] = ep_len;
+      if (autoreset) {
+        E::reset(s, p, rng, obs);
+        ep_len = 0;
+        ep_ret = 0.0;
+      }
+    }
+    if (p.obs) store_obs<real>(p.obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
+    if (p.reward) {
+      const int64_t ro = (ROLL ? t * p.rew_ts : 0) + i;
+      if (p.reward_f32) ((float*)p.reward)[ro] = (float)rew;
+      else ((real*)p.reward)[ro] = rew;
+    }
+    if (p.done) {
+      p.done[(ROLL ? t * p.done_ts : 0) + i] =
+          (uint8_t)((term ? CL_DONE_TERMINATED : 0) | (trunc ? CL_DONE_TRUNCATED : 0));
+    }
+  }
+}
+
+template <class E>
+__device__ __forceinline__ void synth_action(const KParams& p, const Stream& rng, float* a) {
+  const u32x4 r = rng.draw(TAG_ACTION);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int c = 0; c < E::ACT; ++c) a[c] = p.synth_amp * (2.0f * u01_24(w[c & 3]) - 1.0f);
+}
+
+// ---- the static step / rollout kernel: thread i owns env i for the whole launch ----------
 
 template <class E, bool ROLL>
 __global__ void __launch_bounds__(256) k_step(const KParams p) {
-  typedef typename E::real real;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < p.n;
   const unsigned lane = threadIdx.x & 31u;
@@ -151,7 +239,7 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
   const bool want_noise = E::NOISE > 0 && E::uses_noise(p);
   const int T = ROLL ? p.T : 1;
 
-  // actions are fetched one control interval ahead so that their HBM latency hides behind
+  // actions are fetched one control interval ahead so that their HBM latency can hide behind
   // the previous interval's integration (only ~3.5 warps per scheduler at 65,536 envs)
   float a_next[E::ACT];
 #pragma unroll
@@ -159,15 +247,10 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
     a_next[c] = (live && p.action != nullptr) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
 
   for (int t = 0; t < T; ++t) {
-    const uint64_t step = p.step_index + (uint64_t)t;
-    const Stream rng = make_stream(p, i, step);
-
+    const Stream rng = make_stream(p, i, p.step_index + (uint64_t)t);
     float a[E::ACT];
     if (ROLL && p.action == nullptr) {
-      const u32x4 r = rng.draw(TAG_ACTION);
-      const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-      for (int c = 0; c < E::ACT; ++c) a[c] = p.synth_amp * (2.0f * u01_24(w[c & 3]) - 1.0f);
+      synth_action<E>(p, rng, a);
     } else {
 #pragma unroll
       for (int c = 0; c < E::ACT; ++c) a[c] = a_next[c];
@@ -177,77 +260,175 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
           a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
       }
     }
-
-    double nz[E::NOISE > 0 ? E::NOISE : 1];
-    nz[0] = 0.0;
-    if (want_noise) {
-      if (p.noise != nullptr) {
-#pragma unroll
-        for (int c = 0; c < E::NOISE; ++c) nz[c] = live ? p.noise[c * p.n_pad + i] : 0.0;
-      } else {
-        draw_normal<(E::NOISE > 0 ? E::NOISE : 1)>(rng, TAG_NOISE, nz);
-      }
-    }
-
-    real obs[E::OBS];
-    real rew;
-    bool term;
-    E::step(s, p, a, nz, obs, rew, term);
-    ep_len += 1;
-    ep_ret += (double)rew;
-    const bool trunc = E::time_limit(p, ep_len);
-    const bool done = term || trunc;
-    const bool bad = !E::finite(s);
-
-    // warp-aggregated statistics (one set of atomics per warp, only when something ended)
-    const unsigned dm = __ballot_sync(0xffffffffu, live && done && autoreset);
-    const unsigned bm = __ballot_sync(0xffffffffu, live && bad);
-    if (dm) {
-      const bool mine = (dm >> lane) & 1u;
-      const double r1 = warp_sum(mine ? ep_ret : 0.0);
-      const double r2 = warp_sum(mine ? ep_ret * ep_ret : 0.0);
-      const int l1 = warp_sum(mine ? ep_len : 0);
-      const unsigned tm = __ballot_sync(0xffffffffu, mine && term);
-      const unsigned um = __ballot_sync(0xffffffffu, mine && trunc && !term);
-      if (lane == 0) {
-        atomicAdd(&p.stats[CL_STAT_EPISODES], (double)__popc(dm));
-        atomicAdd(&p.stats[CL_STAT_RET_SUM], r1);
-        atomicAdd(&p.stats[CL_STAT_RET_SQ], r2);
-        atomicAdd(&p.stats[CL_STAT_LEN_SUM], (double)l1);
-        if (tm) atomicAdd(&p.stats[CL_STAT_TERMINATED], (double)__popc(tm));
-        if (um) atomicAdd(&p.stats[CL_STAT_TRUNCATED], (double)__popc(um));
-      }
-    }
-    if (bm && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)__popc(bm));
-
-    if (live) {
-      const int64_t oo = ROLL ? t * p.obs_ts : 0;
-      if (done) {
-        if (p.term_obs) store_obs<real>(p.term_obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
-        if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;
-        if (p.last_ep_len) p.last_ep_len[i] = ep_len;
-        if (autoreset) {
-          E::reset(s, p, rng, obs);
-          ep_len = 0;
-          ep_ret = 0.0;
-        }
-      }
-      if (p.obs) store_obs<real>(p.obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
-      if (p.reward) {
-        const int64_t ro = (ROLL ? t * p.rew_ts : 0) + i;
-        if (p.reward_f32) ((float*)p.reward)[ro] = (float)rew;
-        else ((real*)p.reward)[ro] = rew;
-      }
-      if (p.done) {
-        p.done[(ROLL ? t * p.done_ts : 0) + i] =
-            (uint8_t)((term ? CL_DONE_TERMINATED : 0) | (trunc ? CL_DONE_TRUNCATED : 0));
-      }
-    }
+    env_interval<E, ROLL>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset);
   }
   if (live) {
     E::store(s, p, i);
     p.ep_len[i] = ep_len;
     p.ep_return[i] = ep_ret;
+  }
+}
+
+// ---- the dynamic rollout kernel ---------------------------------------------------------
+// At 65,536 envs there are 2048 env-warps for 148 x 4 = 592 warp schedulers: 3.46 each, so a
+// static thread<->env mapping leaves every scheduler waiting for the ones that hold 4 (86.5 %
+// balance; partial warps cost a full FP64 issue, tools/dfma_probe.cu).  Here the launch is cut
+// into tasks (env-warp e, chunk c of `dyn_chunk` control intervals); persistent worker warps
+// (4 per scheduler) pull tasks from an atomic counter in c-major order.  Chunk c of an env-warp
+// may only start after chunk c-1 finished (possibly on another SM): the finishing warp publishes
+// progress[e] with a release store after a device-scope fence, the next one acquires it and
+// reads the state planes with L1-bypassing loads.  A waiting warp only ever waits for a task
+// with a smaller index, which some running (or finished) warp already owns, so the scheme cannot
+// deadlock whatever the residency.
+// The chunk's actions are staged in shared memory by bulk async copies (cp.async.bulk ->
+// UBLKCP, completion on an mbarrier) issued one task ahead: no register scoreboard is involved,
+// which removes the loop-head stall ptxas attaches to prefetching LDGs
+// (profiles/r01_rollout_ncu_source_stalls.txt).
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <class E>
+__global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int Tc = p.dyn_chunk;
+  const int per_buf = Tc * E::ACT * 32;  // floats
+  float* abuf = (float*)dyn_smem + (size_t)wib * per_buf;
+  uint64_t* mbar = (uint64_t*)(dyn_smem + (size_t)wpb * per_buf * sizeof(float)) + wib;
+  const bool tma = p.dyn_tma != 0;
+  if (tma) {
+    if (lane == 0) {
+      mbar_init(&mbar[0], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  const bool obs64 = (p.flags & CL_F_OBS_F64) != 0;
+  const bool autoreset = (p.flags & CL_F_AUTORESET) != 0;
+  const bool want_noise = E::NOISE > 0 && E::uses_noise(p);
+  const uint32_t W = (uint32_t)p.dyn_nwarps, total = W * (uint32_t)p.dyn_nchunks;
+
+  auto grab = [&]() -> uint32_t {
+    uint32_t q = 0;
+    if (lane == 0) q = atomicAdd(p.dyn_counter, 1u);
+    return __shfl_sync(0xffffffffu, q, 0);
+  };
+  // stage the actions of task q into buffer b: lanes 0..len*ACT-1 issue one 128 B copy each
+  auto stage = [&](uint32_t q, int b) {
+    const uint32_t e = q % W, c = q / W;
+    const int t0 = (int)c * Tc;
+    const int len = min(Tc, p.T - t0);
+    if (lane == 0) mbar_expect_tx(&mbar[b], (uint32_t)(len * E::ACT * 128));
+    __syncwarp();
+    if ((int)lane < len * E::ACT) {
+      const int tl = (int)lane / E::ACT, cc = (int)lane % E::ACT;
+      const float* src = p.action + (int64_t)(t0 + tl) * p.act_ts + (int64_t)cc * p.act_cs + (int64_t)e * 32;
+      bulk_g2s(abuf + (size_t)b * per_buf + ((size_t)tl * E::ACT + cc) * 32, src, 128u, &mbar[b]);
+    }
+  };
+
+  // No task is reserved ahead of time: with W env-warps in c-major order and fewer than W
+  // workers, the predecessor (same env-warp, previous chunk) of a freshly grabbed task was
+  // grabbed W grabs -- i.e. W task completions -- earlier, so it has finished and the dependency
+  // wait below practically never spins (a reserve-ahead scheme doubled the in-flight window and
+  // spent 20 % of its samples spinning: profiles/r01_dyn_ncu_source_stalls.txt).
+  uint32_t phase = 0u;
+  uint32_t q = grab();
+  while (q < total) {
+    const uint32_t e = q % W, c = q / W;
+    const int t0 = (int)c * Tc;
+    const int len = min(Tc, p.T - t0);
+    const int64_t i = (int64_t)e * 32 + lane;
+    const bool live = i < p.n;
+    if (tma) {
+      // the staging buffer was last read (generic proxy) by this warp in the previous task
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      stage(q, 0);
+    }
+    if (c > 0) {
+      if (lane == 0) {
+        while (ld_relaxed_u32(p.dyn_progress + e) < c) __nanosleep(32);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      }
+      __syncwarp();
+    }
+    typename E::S s = {};
+    int32_t ep_len = 0;
+    double ep_ret = 0.0;
+    if (live) {
+      E::load(s, p, i);
+      ep_len = __ldcg(p.ep_len + i);
+      ep_ret = __ldcg(p.ep_return + i);
+    }
+    E::prepare(s, p, live);
+    if (tma) {
+      mbar_wait(&mbar[0], phase);
+      phase ^= 1u;
+    }
+    const float* ab = abuf;
+    for (int tl = 0; tl < len; ++tl) {
+      const int t = t0 + tl;
+      const Stream rng = make_stream(p, i, p.step_index + (uint64_t)t);
+      float a[E::ACT];
+      if (p.action == nullptr) {
+        synth_action<E>(p, rng, a);
+      } else if (tma) {
+#pragma unroll
+        for (int cc = 0; cc < E::ACT; ++cc) a[cc] = ab[(tl * E::ACT + cc) * 32 + lane];
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < E::ACT; ++cc)
+          a[cc] = live ? p.action[(int64_t)t * p.act_ts + i * p.act_es + cc * p.act_cs] : 0.0f;
+      }
+      env_interval<E, true>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset);
+    }
+    if (live) {
+      E::store(s, p, i);
+      p.ep_len[i] = ep_len;
+      p.ep_return[i] = ep_ret;
+    }
+    // publish: the warp barrier orders every lane's stores before lane 0's release store
+    __syncwarp();
+    if (lane == 0) st_release_u32(p.dyn_progress + e, c + 1u);
+    q = grab();
   }
 }
 
@@ -288,15 +469,29 @@ cudaError_t launch_env(const KParams& p, int mode, cudaStream_t st, int block) {
     case MODE_ROLLOUT: k_step<E, true><<<grid, block, 0, st>>>(p); break;
     case MODE_RESET: k_reset<E><<<grid, block, 0, st>>>(p); break;
     case MODE_INIT: k_init<E><<<grid, block, 0, st>>>(p); break;
+    case MODE_ROLLOUT_DYN: {
+      // block = 128 threads (one warp per scheduler), p.dyn_grid blocks, smem = action staging
+      const size_t smem = (size_t)4 * p.dyn_chunk * E::ACT * 32 * sizeof(float) + 4 * sizeof(uint64_t);
+      k_rollout_dyn<E><<<(unsigned)p.dyn_grid, 128, smem, st>>>(p);
+      break;
+    }
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 
+template <class E>
+cudaError_t dyn_occupancy(int chunk, int* blocks_per_sm) {
+  const size_t smem = (size_t)4 * chunk * E::ACT * 32 * sizeof(float) + 4 * sizeof(uint64_t);
+  cudaError_t e = cudaFuncSetAttribute(k_rollout_dyn<E>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_rollout_dyn<E>, 128, smem);
+}
+
 // plane accessors
 template <typename real>
 __device__ __forceinline__ real ldp(const KParams& p, int c, int64_t i) {
-  return ((const real*)p.state)[(int64_t)c * p.n_pad + i];
+  return __ldcg((const real*)p.state + (int64_t)c * p.n_pad + i);  // L1-bypassing: see k_rollout_dyn
 }
 template <typename real>
 __device__ __forceinline__ void stp(const KParams& p, int c, int64_t i, real v) {
@@ -310,4 +505,6 @@ cudaError_t cl_launch_parity(int kind, const cl::KParams& p, int mode, cudaStrea
 cudaError_t cl_launch_northstar(int kind, const cl::KParams& p, int mode, cudaStream_t st, int block);
 cudaError_t cl_occupancy_parity(int kind, int block, int* blocks_per_sm);
 cudaError_t cl_occupancy_northstar(int kind, int block, int* blocks_per_sm);
+cudaError_t cl_dyn_occupancy_parity(int kind, int chunk, int* blocks_per_sm);
+cudaError_t cl_dyn_occupancy_northstar(int kind, int chunk, int* blocks_per_sm);
 cudaError_t cl_fma_peak_launch(int dtype_bytes, int grid, int block, int iters, void* sink, cudaStream_t st);

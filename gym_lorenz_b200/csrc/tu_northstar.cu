@@ -27,6 +27,15 @@ cudaError_t cl_occupancy_northstar(int kind, int block, int* out) {
   }
 }
 
+cudaError_t cl_dyn_occupancy_northstar(int kind, int chunk, int* out) {
+  switch (kind) {
+#define X(K, E) case K: return dyn_occupancy<E>(chunk, out);
+    CL_NS_KINDS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 // ---- FMA peak: 8 independent register-resident chains per thread ---------------------
 template <typename R>
 __global__ void __launch_bounds__(256) k_fma_peak(int iters, R* sink) {

@@ -32,6 +32,15 @@ cudaError_t cl_occupancy_parity(int kind, int block, int* out) {
   }
 }
 
+cudaError_t cl_dyn_occupancy_parity(int kind, int chunk, int* out) {
+  switch (kind) {
+#define X(K, E) case K: return dyn_occupancy<E>(chunk, out);
+    CL_PARITY_KINDS(X)
+#undef X
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 // ---- derivative helpers (cl_derivatives) ---------------------------------------------
 // PMSM_Sync_Env._get_derivatives (lorenz_env_try_pmsm.py:51-58), called directly by
 // code/lorenz_pmsm/test_evaluate.py:105-108; hr_derivatives (lorenz_env_try.py:7-12).

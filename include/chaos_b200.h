@@ -246,6 +246,8 @@ int cl_measure_fma_peak(int32_t device, int32_t dtype_bytes, double seconds, dou
 int64_t cl_launch_count(const cl_ctx* ctx);
 /* threads per block the context chose for its env kernels (wave-quantisation aware) */
 int cl_block_size(const cl_ctx* ctx);
+/* cl_rollout calls served by the dynamically scheduled kernel (env-warp x interval-chunk tasks) */
+int64_t cl_dyn_launch_count(const cl_ctx* ctx);
 
 /* -- host-side test hooks (no GPU needed): the exact Philox block and uniform mapping
  *    the kernels use, compiled from the same source. */

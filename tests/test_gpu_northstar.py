@@ -123,3 +123,58 @@ def test_per_env_parameter_randomisation(oracle_api):
     b.reset()
     assert np.array_equal(b.state.cpu().numpy()[6:8], sg[6:8])  # parameters survive reset
     b.close()
+
+
+@pytest.mark.parametrize("kind,n,layout", [
+    ("lorenz_rk4", 65536, "soa"),      # bench shape: bulk-copy (TMA) action staging
+    ("lorenz_rk4", 40000, "soa"),      # partial last warp, padded planes
+    ("lorenz_rk4", 40000, "aos"),      # policy-shaped [T, N, A] actions: LDG path
+    ("lorenz_rk4", 40000, "synth"),    # in-kernel Philox actions
+    ("hr_sync", 33333, "aos"),
+    ("pmsm_sync", 35000, "soa"),
+    ("lorenz3", 34567, "soa"),
+])
+def test_dynamic_rollout_is_bit_identical_to_static(kind, n, layout, monkeypatch):
+    """k_rollout_dyn (env-warp x interval-chunk tasks pulled from an atomic queue, chunks of one
+    env-warp handed between SMs through release/acquire) must reproduce the static kernel."""
+    import torch
+    T = 37   # not a multiple of the chunk (8): exercises the short last chunk
+    kw = dict(seed=13, autoreset=True, max_episode_steps=11)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CHAOS_B200_DYN", mode)
+        b = H.gpu_batch(kind, n, **kw)
+        b.reset()
+        g = torch.Generator(device="cpu").manual_seed(5)
+        amp = 0.05 if kind == "lorenz3" else float(b.layout.act_high)
+        if layout == "soa":
+            soa = ((torch.rand((T, b.act_dim, b.n_pad), generator=g) * 2 - 1) * amp).to(b.device)
+            acts = soa[:, :, :n].permute(0, 2, 1)
+        elif layout == "aos":
+            acts = ((torch.rand((T, n, b.act_dim), generator=g) * 2 - 1) * amp).to(b.device)
+        else:
+            acts = None
+        out = b.rollout(T, acts)
+        torch.cuda.synchronize()
+        assert b.dyn_launch_count == (1 if mode == "1" else 0)
+        res[mode] = (out["obs"].clone(), out["reward"].clone(), out["done"].clone(), b.state.clone(),
+                     b.ep_len.clone(), b.ep_return.clone(), b.stats())
+        b.close()
+    for x, y in zip(res["0"][:6], res["1"][:6]):
+        assert torch.equal(torch.nan_to_num(x[..., :n].double()), torch.nan_to_num(y[..., :n].double()))
+    s0, s1 = res["0"][6], res["1"][6]
+    assert s0["episodes"] == s1["episodes"] and s0["length_sum"] == s1["length_sum"]
+    assert np.isclose(s0["return_sum"], s1["return_sum"], rtol=1e-9)
+
+
+def test_dynamic_rollout_is_selected_automatically_at_65536(monkeypatch):
+    monkeypatch.delenv("CHAOS_B200_DYN", raising=False)
+    b = H.gpu_batch("lorenz_rk4", 65536, seed=1)
+    b.reset()
+    b.rollout(64, want=("reward",))
+    assert b.dyn_launch_count == 1          # 2048 env-warps on 592 schedulers: 86.5 % static balance
+    b2 = H.gpu_batch("lorenz_rk4", 1048576, seed=1)
+    b2.reset()
+    b2.rollout(16, want=("reward",))
+    assert b2.dyn_launch_count == 0         # 32768 env-warps: 98.8 % static balance
+    b.close(); b2.close()
