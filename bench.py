@@ -269,10 +269,21 @@ def run_b200(args):
         flops = float(N) * T * S * FLOP_PER_SUBSTEP
         ach = flops / (kern_ms * 1e-3) * 1e-12
         gbs = float(N) * T * BYTES_PER_ENV_STEP / (kern_ms * 1e-3) * 1e-9
+        dyn = batch.dyn_launch_count > 0
+        traffic = None
+        try:   # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            w = tj["workload"]
+            if (w["kind"], w["envs"], w["chunk"], w["substeps"]) == (args.kind, N, T, S) and dyn:
+                traffic = {"bytes": tj["dram_bytes_read"] + tj["dram_bytes_write"], "algorithmic_bytes": int(N) * T * BYTES_PER_ENV_STEP,
+                           "source": tj["source"]}
+        except Exception:  # noqa: BLE001
+            pass
         roofline = {
-            "kernel": "cl::k_step<EnvLorenzRK4<double>, ROLL=true> (fused T-interval rollout)",
+            "kernel": ("cl::k_rollout_dyn<EnvLorenzRK4<double>> (fused T-interval rollout, env-warp x chunk tasks)" if dyn
+                       else "cl::k_step<EnvLorenzRK4<double>, ROLL=true> (fused T-interval rollout)"),
             "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": ach / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+            "frac": ach / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
             "peak_source": "DFMA-chain micro-kernel (cl_measure_fma_peak) run in this process, 2 flop/FMA; "
                            "MEASURED_PEAKS.json has no FP64 entry",
             "algorithmic_flop_per_substep": FLOP_PER_SUBSTEP,

@@ -33,6 +33,7 @@ const int CL_DYN_CHUNK_DEFAULT = 8;
 const int kHostRing = 3;  // pinned output slots: obs returned at step t stays valid through t+2
 
 struct HostSlot {
+  unsigned char* out;  // pinned, same layout as HostStage::d_out
   float* obs;
   float* reward;
   uint8_t* done;
@@ -45,9 +46,11 @@ struct HostStage {
   bool ready;
   float* h_act;   // pinned [N][A]
   float* d_act;   // device [N][A]
-  float* d_obs;   // device [N][O]
-  float* d_rew;   // device [n_pad] f32
+  unsigned char* d_out;  // device, one block: [obs N*O f32 | reward N f32 | done N u8] -> ONE D2H copy
+  float* d_obs;   // = d_out
+  float* d_rew;   // = d_out + N*O*4
   uint8_t* d_done;
+  size_t out_bytes;
   float* d_term;  // device [N][O]
   double* d_ler;
   int32_t* d_lel;
@@ -184,10 +187,10 @@ static void host_stage_free(cl_ctx* ctx) {
   HostStage& h = ctx->hs;
   if (!h.ready) return;
   cudaFreeHost(h.h_act);
-  cudaFree(h.d_act); cudaFree(h.d_obs); cudaFree(h.d_rew); cudaFree(h.d_done);
+  cudaFree(h.d_act); cudaFree(h.d_out);
   cudaFree(h.d_term); cudaFree(h.d_ler); cudaFree(h.d_lel);
   for (int k = 0; k < kHostRing; ++k) {
-    cudaFreeHost(h.slot[k].obs); cudaFreeHost(h.slot[k].reward); cudaFreeHost(h.slot[k].done);
+    cudaFreeHost(h.slot[k].out);
     cudaFreeHost(h.slot[k].term_obs); cudaFreeHost(h.slot[k].last_ep_ret); cudaFreeHost(h.slot[k].last_ep_len);
   }
   cudaStreamDestroy(h.stream);
@@ -307,7 +310,7 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
   cudaStream_t st = (cudaStream_t)stream;
   CU(cudaSetDevice(ctx->cfg.device));
   int chunk = CL_DYN_CHUNK_DEFAULT;
-  if (const char* ov = getenv("CHAOS_B200_DYN_CHUNK")) { const int c = atoi(ov); if (c >= 1 && c <= 32) chunk = c; }
+  if (const char* ov = getenv("CHAOS_B200_DYN_CHUNK")) { const int c = atoi(ov); if (c >= 1 && c <= 16) chunk = c; }
   int mode = cl::MODE_ROLLOUT;
   if (want_dynamic(ctx, d->T, chunk)) {
     const int64_t W = (ctx->cfg.num_envs + 31) / 32;
@@ -392,9 +395,11 @@ static int host_stage_init(cl_ctx* ctx) {
   CU(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
   CU(cudaHostAlloc((void**)&h.h_act, N * A * sizeof(float), cudaHostAllocDefault));
   CU(cudaMalloc((void**)&h.d_act, N * A * sizeof(float)));
-  CU(cudaMalloc((void**)&h.d_obs, N * O * sizeof(float)));
-  CU(cudaMalloc((void**)&h.d_rew, NP * sizeof(float)));
-  CU(cudaMalloc((void**)&h.d_done, NP));
+  h.out_bytes = N * O * sizeof(float) + N * sizeof(float) + N;
+  CU(cudaMalloc((void**)&h.d_out, h.out_bytes));
+  h.d_obs = (float*)h.d_out;
+  h.d_rew = (float*)(h.d_out + N * O * sizeof(float));
+  h.d_done = (uint8_t*)(h.d_out + N * O * sizeof(float) + N * sizeof(float));
   CU(cudaMalloc((void**)&h.d_term, N * O * sizeof(float)));
   CU(cudaMalloc((void**)&h.d_ler, NP * sizeof(double)));
   CU(cudaMalloc((void**)&h.d_lel, NP * sizeof(int32_t)));
@@ -402,9 +407,10 @@ static int host_stage_init(cl_ctx* ctx) {
   CU(cudaMemset(h.d_ler, 0, NP * sizeof(double)));
   CU(cudaMemset(h.d_lel, 0, NP * sizeof(int32_t)));
   for (int k = 0; k < kHostRing; ++k) {
-    CU(cudaHostAlloc((void**)&h.slot[k].obs, N * O * sizeof(float), cudaHostAllocDefault));
-    CU(cudaHostAlloc((void**)&h.slot[k].reward, N * sizeof(float), cudaHostAllocDefault));
-    CU(cudaHostAlloc((void**)&h.slot[k].done, N, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&h.slot[k].out, h.out_bytes, cudaHostAllocDefault));
+    h.slot[k].obs = (float*)h.slot[k].out;
+    h.slot[k].reward = (float*)(h.slot[k].out + N * O * sizeof(float));
+    h.slot[k].done = (uint8_t*)(h.slot[k].out + N * O * sizeof(float) + N * sizeof(float));
     CU(cudaHostAlloc((void**)&h.slot[k].term_obs, N * O * sizeof(float), cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&h.slot[k].last_ep_ret, N * sizeof(double), cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&h.slot[k].last_ep_len, N * sizeof(int32_t), cudaHostAllocDefault));
@@ -456,9 +462,7 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
   ctx->step_index += 1;
   h.cur = (h.cur + 1) % kHostRing;
   HostSlot& s = h.slot[h.cur];
-  CU(cudaMemcpyAsync(s.obs, h.d_obs, N * O * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(s.reward, h.d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(s.done, h.d_done, N, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(s.out, h.d_out, h.out_bytes, cudaMemcpyDeviceToHost, st));
   h.pending = true;
   return CL_OK;
 }

@@ -140,7 +140,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
                                              const KParams& p, const int64_t i, const bool live,
                                              const unsigned lane, const int t, const Stream& rng,
                                              const float* a, const bool want_noise, const bool obs64,
-                                             const bool autoreset) {
+                                             const bool autoreset, unsigned& bad_acc) {
   typedef typename E::real real;
   double nz[E::NOISE > 0 ? E::NOISE : 1];
   nz[0] = 0.0;
@@ -182,7 +182,8 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
       if (um) atomicAdd(&p.stats[CL_STAT_TRUNCATED], (double)__popc(um));
     }
   }
-  if (bm && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)__popc(bm));
+  bad_acc += __popc(bm);  // flushed once per launch / task (diverged envs would otherwise
+                          // serialise every warp on one atomic each interval)
 
   if (live) {
     const int64_t oo = ROLL ? t * p.obs_ts : 0;
@@ -246,6 +247,7 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
   for (int c = 0; c < E::ACT; ++c)
     a_next[c] = (live && p.action != nullptr) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
 
+  unsigned bad_acc = 0u;
   for (int t = 0; t < T; ++t) {
     const Stream rng = make_stream(p, i, p.step_index + (uint64_t)t);
     float a[E::ACT];
@@ -260,8 +262,9 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
           a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
       }
     }
-    env_interval<E, ROLL>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset);
+    env_interval<E, ROLL>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc);
   }
+  if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
   if (live) {
     E::store(s, p, i);
     p.ep_len[i] = ep_len;
@@ -358,8 +361,8 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     const int len = min(Tc, p.T - t0);
     if (lane == 0) mbar_expect_tx(&mbar[b], (uint32_t)(len * E::ACT * 128));
     __syncwarp();
-    if ((int)lane < len * E::ACT) {
-      const int tl = (int)lane / E::ACT, cc = (int)lane % E::ACT;
+    for (int k = (int)lane; k < len * E::ACT; k += 32) {  // every expected byte must be issued
+      const int tl = k / E::ACT, cc = k % E::ACT;
       const float* src = p.action + (int64_t)(t0 + tl) * p.act_ts + (int64_t)cc * p.act_cs + (int64_t)e * 32;
       bulk_g2s(abuf + (size_t)b * per_buf + ((size_t)tl * E::ACT + cc) * 32, src, 128u, &mbar[b]);
     }
@@ -404,6 +407,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
       phase ^= 1u;
     }
     const float* ab = abuf;
+    unsigned bad_acc = 0u;
     for (int tl = 0; tl < len; ++tl) {
       const int t = t0 + tl;
       const Stream rng = make_stream(p, i, p.step_index + (uint64_t)t);
@@ -418,8 +422,10 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
         for (int cc = 0; cc < E::ACT; ++cc)
           a[cc] = live ? p.action[(int64_t)t * p.act_ts + i * p.act_es + cc * p.act_cs] : 0.0f;
       }
-      env_interval<E, true>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset);
+      env_interval<E, true>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc);
     }
+    if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
+    bad_acc = 0u;
     if (live) {
       E::store(s, p, i);
       p.ep_len[i] = ep_len;
