@@ -127,7 +127,7 @@ def cpu_arm(args, budget_s):
     Returns (env_steps_per_s, cores, sample_text, T_sample, elapsed)."""
     from oracle import api as O
     n = args.envs_per_gpu
-    threads = min(O.max_threads(), len(os.sched_getaffinity(0)))
+    threads = len(os.sched_getaffinity(0))   # all host cores, whatever OMP_NUM_THREADS torchrun exported
     O.set_threads(threads)
     orc = O.Oracle(args.kind, n, flags=O.F_AUTORESET, seed=0, substeps=args.substeps, dt=0.01,
                    act_limit=1.0, act_gain=50.0, max_episode_steps=1000)
@@ -147,7 +147,7 @@ def run_reference(args):
         return
     from oracle import api as O
     n = args.envs_per_gpu
-    threads = min(O.max_threads(), len(os.sched_getaffinity(0)))
+    threads = len(os.sched_getaffinity(0))   # all host cores, whatever OMP_NUM_THREADS torchrun exported
     O.set_threads(threads)
     orc = O.Oracle(args.kind, n, flags=O.F_AUTORESET, seed=0, substeps=args.substeps, dt=0.01,
                    act_limit=1.0, act_gain=50.0, max_episode_steps=1000)

@@ -17,11 +17,12 @@ CL_ABI_VERSION = 1
 # env kinds (cl_env_kind)
 LORENZ3, LORENZ3_PAIR, LORENZ4_PAIR, HR_SYNC, PMSM_SYNC, PMSM_CLASSIC, PMSM_SINGLE = range(7)
 LORENZ_RK4, LORENZ_RK4_F32, PMSM_RK4 = 7, 8, 9
+MEMRISTIVE4_PAIR, PMSM_FREE = 10, 11
 KIND_NAMES = {
     "lorenz3": LORENZ3, "lorenz3_pair": LORENZ3_PAIR, "lorenz4_pair": LORENZ4_PAIR,
     "hr_sync": HR_SYNC, "pmsm_sync": PMSM_SYNC, "pmsm_classic": PMSM_CLASSIC,
     "pmsm_single": PMSM_SINGLE, "lorenz_rk4": LORENZ_RK4, "lorenz_rk4_f32": LORENZ_RK4_F32,
-    "pmsm_rk4": PMSM_RK4,
+    "pmsm_rk4": PMSM_RK4, "memristive4_pair": MEMRISTIVE4_PAIR, "pmsm_free": PMSM_FREE,
 }
 
 F_ADD_NOISE, F_EVAL_MODE, F_ADD_FILTER, F_AUTORESET, F_OBS_F64 = 0x01, 0x02, 0x04, 0x08, 0x10
@@ -114,6 +115,13 @@ SYMBOLS = [
     ("cl_launch_count", C.c_int64, [_VP]),
     ("cl_block_size", C.c_int, [_VP]),
     ("cl_dyn_launch_count", C.c_int64, [_VP]),
+    ("cl_gae", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_double, C.c_double, C.c_int32, C.c_int64, C.c_int64, _VP, _VP]),
+    ("cl_obs_moments", C.c_int, [_VP, _VP, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _VP, _VP]),
+    ("cl_obs_normalize", C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                   _VP, _VP, C.c_double, C.c_double]),
+    ("cl_frame_stack", C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_int64, _VP, C.c_int64, C.c_int32, C.c_int32]),
+    ("cl_eval_metrics", C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32,
+                                  C.c_double, C.c_double, _VP]),
     ("cl_philox4x32_10", None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("cl_uniform53", C.c_double, [C.c_uint32, C.c_uint32, C.c_double, C.c_double]),
 ]

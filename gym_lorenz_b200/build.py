@@ -49,6 +49,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     units = [
         ("tu_parity.cu", ["-fmad=false"]),
         ("tu_northstar.cu", []),
+        ("tu_rl_ops.cu", ["-fmad=false"]),
         ("chaos_b200.cu", []),
     ]
     objs = []

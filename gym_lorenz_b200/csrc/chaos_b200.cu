@@ -27,6 +27,8 @@ const cl_layout kLayouts[CL_ENV_KIND_COUNT] = {
     /* LORENZ_RK4    */ {8, 6, 0, 6, 3, 0, -1.0, 1.0, -HUGE_VAL, HUGE_VAL, 1000, 0},
     /* LORENZ_RK4_F32*/ {4, 6, 0, 6, 3, 0, -1.0, 1.0, -HUGE_VAL, HUGE_VAL, 1000, 0},
     /* PMSM_RK4      */ {8, 8, 0, 6, 2, 0, -1.0, 1.0, -HUGE_VAL, HUGE_VAL, 2000, 0},
+    /* MEMRISTIVE4   */ {8, 9, 0, 8, 3, 0, -2.0, 2.0, -HUGE_VAL, HUGE_VAL, 0, 0},
+    /* PMSM_FREE     */ {8, 4, 0, 6, 2, 3, -100.0, 100.0, -HUGE_VAL, HUGE_VAL, 0, 0},
 };
 
 const int CL_DYN_CHUNK_DEFAULT = 8;
@@ -98,7 +100,7 @@ static int fail(cl_ctx* ctx, int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                    \
   } while (0)
 
-static bool is_parity(int kind) { return kind >= CL_ENV_LORENZ3 && kind <= CL_ENV_PMSM_SINGLE; }
+static bool is_parity(int kind) { return !(kind >= CL_ENV_LORENZ_RK4 && kind <= CL_ENV_PMSM_RK4); }
 
 // Threads on the most loaded SM decide the duration of a single partial wave; pick the block
 // size that minimises ceil(blocks / SMs) * block (ties -> larger block).  65,536 envs on 148

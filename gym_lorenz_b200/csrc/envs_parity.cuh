@@ -574,4 +574,122 @@ struct EnvPMSMSingle {
   }
 };
 
+// ====================================================================================
+// CL_ENV_MEMRISTIVE4_PAIR -- lorenz_env_transient2.py: two 4-state memristive systems
+// (a=30, b=1, c=36, d=0.5, h=0.003), Euler dt 0.001; the slave gets u*100 (float32 product) on
+// dx1, dx2, dx4.  planes: a0..a3 b0..b3 t
+__device__ __forceinline__ void memristive4_rhs(const double* s, double* d) {
+  const double w = (2.0 * s[3]) * s[3];
+  d[0] = 30.0 * ((w * (s[1] - s[0])) + (0.5 * s[0]));
+  d[1] = 1.0 * ((w * (s[0] - s[1])) - s[2]);
+  d[2] = 36.0 * (s[1] - (0.003 * s[2]));
+  d[3] = (s[1] - s[0]) - (0.01 * s[3]);
+}
+
+struct EnvMemristive4Pair {
+  typedef double real;
+  enum { NSTATE = 9, NINT = 0, OBS = 8, ACT = 3, NOISE = 0 };
+  struct S { double a[4], b[4], t; };
+  __device__ static void load(S& s, const KParams& p, int64_t i) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { s.a[c] = ldp<double>(p, c, i); s.b[c] = ldp<double>(p, 4 + c, i); }
+    s.t = ldp<double>(p, 8, i);
+  }
+  __device__ static void store(const S& s, const KParams& p, int64_t i) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { stp<double>(p, c, i, s.a[c]); stp<double>(p, 4 + c, i, s.b[c]); }
+    stp<double>(p, 8, i, s.t);
+  }
+  __device__ static bool uses_noise(const KParams&) { return false; }
+  __device__ static bool finite(const S& s) {
+    return isfinite(s.a[0] + s.a[1] + s.a[2] + s.a[3] + s.b[0] + s.b[1] + s.b[2] + s.b[3]);
+  }
+  __device__ static bool time_limit(const KParams& p, int32_t n) {
+    return p.max_steps > 0 && n >= p.max_steps;
+  }
+  __device__ static void prepare(S&, const KParams&, bool) {}
+  __device__ static void init_persistent(S&, const KParams&, const Stream&) {}
+  __device__ static void observe(const S& s, double* obs) {
+    double da[4], db[4];
+    memristive4_rhs(s.a, da);
+    memristive4_rhs(s.b, db);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { obs[c] = s.a[c] - s.b[c]; obs[4 + c] = da[c] - db[c]; }
+  }
+  __device__ static void reset(S& s, const KParams&, const Stream& rng, double* obs) {
+    double u[8];
+    draw_uniform<8>(rng, TAG_RESET, 0.0, 5.0, u);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { s.a[c] = u[c]; s.b[c] = u[4 + c]; }
+    s.t = 0.0;
+    observe(s, obs);
+  }
+  __device__ static void step(S& s, const KParams&, const float* act, const double*, double* obs,
+                              double& rew, bool& term) {
+    const double u1 = (double)__fmul_rn(clipf(act[0], -2.0f, 2.0f), 100.0f);
+    const double u2 = (double)__fmul_rn(clipf(act[1], -2.0f, 2.0f), 100.0f);
+    const double u3 = (double)__fmul_rn(clipf(act[2], -2.0f, 2.0f), 100.0f);
+    double d[4];
+    memristive4_rhs(s.a, d);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s.a[c] = s.a[c] + (d[c] * 0.001);
+    memristive4_rhs(s.b, d);
+    d[0] = d[0] + u1; d[1] = d[1] + u2; d[3] = d[3] + u3;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s.b[c] = s.b[c] + (d[c] * 0.001);
+    observe(s, obs);
+    const double E = (((0.0 + fabs(obs[0])) + fabs(obs[1])) + fabs(obs[2])) + fabs(obs[3]);
+    rew = (-E) - pow(E, 1.0 / 3);
+    s.t = s.t + 0.001;
+    term = (s.t == 5.0) || (rew < -1e6);
+  }
+};
+
+// ====================================================================================
+// CL_ENV_PMSM_FREE -- lorenz_singlecontrol.py: one uncontrolled PMSM with N(0,3) noise in the
+// derivative; `step()` takes no action; `reset()` always starts at (25, 1, -1).  planes: x y z t
+struct EnvPMSMFree {
+  typedef double real;
+  enum { NSTATE = 4, NINT = 0, OBS = 6, ACT = 2, NOISE = 3 };
+  struct S { double x, y, z, t; };
+  __device__ static void load(S& s, const KParams& p, int64_t i) {
+    s.x = ldp<double>(p, 0, i); s.y = ldp<double>(p, 1, i);
+    s.z = ldp<double>(p, 2, i); s.t = ldp<double>(p, 3, i);
+  }
+  __device__ static void store(const S& s, const KParams& p, int64_t i) {
+    stp<double>(p, 0, i, s.x); stp<double>(p, 1, i, s.y);
+    stp<double>(p, 2, i, s.z); stp<double>(p, 3, i, s.t);
+  }
+  __device__ static bool uses_noise(const KParams&) { return true; }
+  __device__ static bool finite(const S& s) { return isfinite(s.x + s.y + s.z); }
+  __device__ static bool time_limit(const KParams& p, int32_t n) {
+    return p.max_steps > 0 && n >= p.max_steps;
+  }
+  __device__ static void prepare(S&, const KParams&, bool) {}
+  __device__ static void init_persistent(S&, const KParams&, const Stream&) {}
+  __device__ static void observe(const S& s, double* obs) {
+    obs[0] = s.x; obs[1] = s.y; obs[2] = s.z;
+    pmsm64_rhs(s.x, s.y, s.z, obs[3], obs[4], obs[5]);
+  }
+  __device__ static void reset(S& s, const KParams&, const Stream&, double* obs) {
+    s.x = 25.0; s.y = 1.0; s.z = -1.0; s.t = 0.0;
+    observe(s, obs);
+  }
+  __device__ static void step(S& s, const KParams&, const float*, const double* nz, double* obs,
+                              double& rew, bool& term) {
+    double dx, dy, dz;
+    pmsm64_rhs(s.x, s.y, s.z, dx, dy, dz);
+    dx = dx + (0.0 + 3.0 * nz[0]);
+    dy = dy + (0.0 + 3.0 * nz[1]);
+    dz = dz + (0.0 + 3.0 * nz[2]);
+    s.x = s.x + (dx * 0.01);
+    s.y = s.y + (dy * 0.01);
+    s.z = s.z + (dz * 0.01);
+    observe(s, obs);
+    rew = -(((0.0 + fabs(obs[0])) + fabs(obs[1])) + fabs(obs[2]));
+    s.t = s.t + 0.01;
+    term = (s.t == 1000.0);
+  }
+};
+
 }  // namespace cl

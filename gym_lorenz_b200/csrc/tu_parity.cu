@@ -12,7 +12,9 @@ using namespace cl;
   X(CL_ENV_HR_SYNC, EnvHRSync)                \
   X(CL_ENV_PMSM_SYNC, EnvPMSMSync)            \
   X(CL_ENV_PMSM_CLASSIC, EnvPMSMClassic)      \
-  X(CL_ENV_PMSM_SINGLE, EnvPMSMSingle)
+  X(CL_ENV_PMSM_SINGLE, EnvPMSMSingle)        \
+  X(CL_ENV_MEMRISTIVE4_PAIR, EnvMemristive4Pair) \
+  X(CL_ENV_PMSM_FREE, EnvPMSMFree)
 
 cudaError_t cl_launch_parity(int kind, const KParams& p, int mode, cudaStream_t st, int block) {
   switch (kind) {
@@ -93,6 +95,7 @@ cudaError_t cl_launch_derivatives(int kind, const void* state, const float* acti
     case CL_ENV_LORENZ3:
     case CL_ENV_LORENZ3_PAIR: k_deriv_lorenz3<<<grid, block, 0, st>>>((const double*)state, (double*)out, n); break;
     case CL_ENV_PMSM_CLASSIC:
+    case CL_ENV_PMSM_FREE:
     case CL_ENV_PMSM_SINGLE: k_deriv_pmsm64<<<grid, block, 0, st>>>((const double*)state, (double*)out, n); break;
     case CL_ENV_LORENZ4_PAIR: k_deriv_lorenz4<<<grid, block, 0, st>>>((const double*)state, (double*)out, n); break;
     default: return cudaErrorInvalidValue;

@@ -1,0 +1,208 @@
+// Device-side versions of the SB3 machinery that sits directly around the env step in the
+// reference's pipelines, so that observations / rewards never leave HBM:
+//   * GAE(lambda)            -- stable_baselines3 2.7.1 RolloutBuffer.compute_returns_and_advantage
+//                               (un-vendored; driven by code/train.py:112-120, gae_lambda=0.95)
+//   * VecNormalize           -- running mean/var update + normalise + clip
+//                               (code/lorenz_pmsm/train.py:118,170: norm_obs=True, clip_obs=10)
+//   * VecFrameStack          -- code/lorenz_filter/train.py:115 (n_stack=4)
+//   * evaluation metrics     -- code/lorenz_pmsm/test_evaluate.py:25-59,239-250,
+//                               code/test_evaluate.py:136-145 (steady-state MAE/RMSE, settling
+//                               time, control energy)
+// All four are HBM-bound streaming kernels: one thread per env (coalesced [T][n] planes).
+// Built with -fmad=false so that the float32 GAE recurrence rounds exactly like NumPy's.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/chaos_b200.h"
+
+namespace {
+
+// ---- GAE -------------------------------------------------------------------------------
+// for step in reversed(range(T)):
+//   nnt, nv = (1 - dones, last_values) if step == T-1 else (1 - episode_starts[step+1], values[step+1])
+//   delta = rewards[step] + gamma * nv * nnt - values[step]
+//   last = delta + gamma * gae_lambda * nnt * last
+//   advantages[step] = last
+// returns = advantages + values          (all float32; gamma, gamma*lambda weak scalars -> f32)
+__global__ void __launch_bounds__(256) k_gae(const float* __restrict__ rew, const float* __restrict__ val,
+                                             const float* __restrict__ starts, const float* __restrict__ last_val,
+                                             const float* __restrict__ last_done, float gamma, float gl, int T,
+                                             int64_t n, int64_t stride, float* __restrict__ adv,
+                                             float* __restrict__ ret) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float last = 0.0f;
+  float nnt = __fsub_rn(1.0f, last_done[i]);
+  float nv = last_val[i];
+  for (int t = T - 1; t >= 0; --t) {
+    const int64_t o = (int64_t)t * stride + i;
+    const float v = val[o];
+    const float delta = __fsub_rn(__fadd_rn(rew[o], __fmul_rn(__fmul_rn(gamma, nv), nnt)), v);
+    last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
+    adv[o] = last;
+    ret[o] = __fadd_rn(last, v);
+    nnt = __fsub_rn(1.0f, starts[o]);
+    nv = v;
+  }
+}
+
+// ---- running moments: per-feature sum(x - shift) and sum((x - shift)^2) over envs --------
+template <int MAXD>
+__global__ void __launch_bounds__(256) k_moments(const float* __restrict__ obs, int64_t es, int64_t cs, int64_t n,
+                                                 int dim, const double* __restrict__ shift, double* __restrict__ out) {
+  double s1[MAXD], s2[MAXD];
+#pragma unroll
+  for (int c = 0; c < MAXD; ++c) { s1[c] = 0.0; s2[c] = 0.0; }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < MAXD; ++c) {
+      if (c < dim) {
+        const double d = (double)obs[i * es + c * cs] - shift[c];
+        s1[c] += d;
+        s2[c] += d * d;
+      }
+    }
+  }
+  const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int c = 0; c < MAXD; ++c) {
+    if (c < dim) {
+      double a = s1[c], b = s2[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (lane == 0) { atomicAdd(&out[c], a); atomicAdd(&out[dim + c], b); }
+    }
+  }
+}
+
+// ---- normalise + clip: clip((x - mean) / sqrt(var + eps), -clip, clip).astype(float32) ----
+__global__ void __launch_bounds__(256) k_normalize(const float* __restrict__ in, int64_t ies, int64_t ics,
+                                                   float* __restrict__ out, int64_t oes, int64_t ocs, int64_t n,
+                                                   int dim, const double* __restrict__ mean,
+                                                   const double* __restrict__ var, double eps, double clip) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c = 0; c < dim; ++c) {
+    double z = ((double)in[i * ies + c * ics] - mean[c]) / sqrt(var[c] + eps);
+    z = z < -clip ? -clip : (z > clip ? clip : z);
+    out[i * oes + c * ocs] = (float)z;
+  }
+}
+
+// ---- frame stack (SB3 StackedObservations, 1-D observations stacked along the last axis) --
+// stacked[i] = roll(stacked[i], -dim); if done[i]: stacked[i] = 0; stacked[i, -dim:] = obs[i]
+__global__ void __launch_bounds__(256) k_frame_stack(float* __restrict__ stacked, const float* __restrict__ obs,
+                                                     int64_t es, int64_t cs, const uint8_t* __restrict__ done,
+                                                     int64_t n, int dim, int k) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float* row = stacked + i * (int64_t)(dim * k);
+  const bool d = done != nullptr && done[i] != 0;
+  for (int j = 0; j < dim * (k - 1); ++j) row[j] = d ? 0.0f : row[j + dim];
+  for (int c = 0; c < dim; ++c) row[dim * (k - 1) + c] = obs[i * es + c * cs];
+}
+
+// ---- evaluation metrics over stored trajectories err[T][3][stride], u[T][2][stride] (f64) ---
+// out[i][8] = mae, rmse, settling_time (NaN = never settles), energy, mae_c0..2 ... see header
+__global__ void __launch_bounds__(256) k_eval_metrics(const double* __restrict__ err, const double* __restrict__ u,
+                                                      int T, int ncomp, int nctrl, int64_t n, int64_t stride,
+                                                      int steady_start, double dt, double band,
+                                                      double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double sa[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, en = 0.0;
+  int last_ex[4] = {-1, -1, -1, -1};
+  for (int t = 0; t < T; ++t) {
+    for (int c = 0; c < ncomp; ++c) {
+      const double e = err[((int64_t)t * ncomp + c) * stride + i];
+      if (fabs(e) > band) last_ex[c] = t;
+      if (t >= steady_start) { sa[c] += fabs(e); sq[c] += e * e; }
+    }
+    double q = 0.0;
+    for (int c = 0; c < nctrl; ++c) {
+      const double a = u[((int64_t)t * nctrl + c) * stride + i];
+      q += a * a;
+    }
+    en += q;
+  }
+  const double m = (double)(T - steady_start);
+  double mae = 0.0, rmse = 0.0, ts = -1.0;
+  bool never = false;
+  for (int c = 0; c < ncomp; ++c) {
+    mae += sa[c] / m;
+    rmse += sqrt(sq[c] / m);
+    if (last_ex[c] + 1 >= T) never = true;                       // np.nan for that component
+    const double tc = (last_ex[c] < 0) ? 0.0 : (double)(last_ex[c] + 1) * dt;
+    if (last_ex[c] + 1 < T && tc > ts) ts = tc;                   // np.nanmax ignores the NaNs
+  }
+  double* o = out + i * 4;
+  o[0] = mae / ncomp;
+  o[1] = rmse / ncomp;
+  o[2] = (ts < 0.0 && never) ? nan("") : (ts < 0.0 ? 0.0 : ts);
+  o[3] = en * dt;
+}
+
+int fail_if(cudaError_t e) { return e == cudaSuccess ? CL_OK : CL_ECUDA; }
+
+}  // namespace
+
+extern "C" int cl_gae(void* stream, const float* rewards, const float* values, const float* episode_starts,
+                      const float* last_values, const float* last_dones, double gamma, double gae_lambda,
+                      int32_t T, int64_t n, int64_t stride, float* advantages, float* returns) {
+  if (!rewards || !values || !episode_starts || !last_values || !last_dones || !advantages || !returns || T < 1 || n < 1)
+    return CL_EINVAL;
+  const int block = 128;
+  k_gae<<<(unsigned)((n + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
+      rewards, values, episode_starts, last_values, last_dones, (float)gamma, (float)(gamma * gae_lambda), T, n,
+      stride, advantages, returns);
+  return fail_if(cudaGetLastError());
+}
+
+extern "C" int cl_obs_moments(void* stream, const float* obs, int64_t es, int64_t cs, int64_t n, int32_t dim,
+                              const double* shift, double* out2d) {
+  if (!obs || !shift || !out2d || dim < 1 || dim > 32 || n < 1) return CL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out2d, 0, sizeof(double) * 2 * (size_t)dim, st);
+  if (e != cudaSuccess) return CL_ECUDA;
+  const int block = 256;
+  int64_t blocks = (n + block - 1) / block;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dim <= 8) k_moments<8><<<(unsigned)blocks, block, 0, st>>>(obs, es, cs, n, dim, shift, out2d);
+  else k_moments<32><<<(unsigned)blocks, block, 0, st>>>(obs, es, cs, n, dim, shift, out2d);
+  return fail_if(cudaGetLastError());
+}
+
+extern "C" int cl_obs_normalize(void* stream, const float* in, int64_t ies, int64_t ics, float* out, int64_t oes,
+                                int64_t ocs, int64_t n, int32_t dim, const double* mean, const double* var,
+                                double epsilon, double clip) {
+  if (!in || !out || !mean || !var || dim < 1 || n < 1) return CL_EINVAL;
+  const int block = 256;
+  k_normalize<<<(unsigned)((n + block - 1) / block), block, 0, (cudaStream_t)stream>>>(in, ies, ics, out, oes, ocs,
+                                                                                         n, dim, mean, var, epsilon, clip);
+  return fail_if(cudaGetLastError());
+}
+
+extern "C" int cl_frame_stack(void* stream, float* stacked, const float* obs, int64_t es, int64_t cs,
+                              const uint8_t* done, int64_t n, int32_t dim, int32_t n_stack) {
+  if (!stacked || !obs || dim < 1 || n_stack < 1 || n < 1) return CL_EINVAL;
+  const int block = 256;
+  k_frame_stack<<<(unsigned)((n + block - 1) / block), block, 0, (cudaStream_t)stream>>>(stacked, obs, es, cs, done, n,
+                                                                                           dim, n_stack);
+  return fail_if(cudaGetLastError());
+}
+
+extern "C" int cl_eval_metrics(void* stream, const double* err, const double* ctrl, int32_t T, int32_t n_err,
+                               int32_t n_ctrl, int64_t n, int64_t stride, int32_t steady_start, double dt,
+                               double error_band, double* out4) {
+  if (!err || !ctrl || !out4 || T < 1 || n_err < 1 || n_err > 4 || n_ctrl < 0 || n < 1 || steady_start < 0 ||
+      steady_start >= T)
+    return CL_EINVAL;
+  const int block = 128;
+  k_eval_metrics<<<(unsigned)((n + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
+      err, ctrl, T, n_err, n_ctrl, n, stride, steady_start, dt, error_band, out4);
+  return fail_if(cudaGetLastError());
+}

@@ -180,6 +180,26 @@ class PMSMSingleEnv(_OldGymGetters, _SingleEnv):
         return np.zeros(6)
 
 
+class Memristive4PairEnv(_OldGymGetters, _SingleEnv):
+    """lorenz_env_transient2.py::lorenzEnv_transient."""
+    KIND, OLD_GYM = "memristive4_pair", True
+
+    def get_current3(self):
+        return self._pair(3)
+
+
+class PMSMFreeEnv(_OldGymGetters, _SingleEnv):
+    """lorenz_singlecontrol.py::lorenzEnv_transient -- `step()` takes no action."""
+    KIND, OLD_GYM = "pmsm_free", True
+
+    @property
+    def state2(self):
+        return np.zeros(6)
+
+    def step(self, action=None):  # noqa: D401 - reference signature is step(self)
+        return super().step(np.zeros(2, np.float32))
+
+
 class HRSyncEnv(_SingleEnv):
     """lorenz_env_try.py::HRSyncEnv(add_noise=False, eval_mode=False, add_filter=False)."""
     KIND = "hr_sync"

@@ -132,6 +132,8 @@ ATTR_PLANES = {
     "lorenz_rk4": {"state1": (0, 3), "sigma": (3, 4), "rho": (4, 5), "beta": (5, 6)},
     "lorenz_rk4_f32": {"state1": (0, 3), "sigma": (3, 4), "rho": (4, 5), "beta": (5, 6)},
     "pmsm_rk4": {"state1": (0, 3), "state2": (3, 6), "sigma": (6, 7), "gamma": (7, 8)},
+    "memristive4_pair": {"state1": (0, 4), "state2": (4, 8), "t": (8, 9)},
+    "pmsm_free": {"state1": (0, 3), "t": (3, 4)},
 }
 _SCALAR_ATTRS = {"t", "sigma", "lambda_coef", "m_t", "v_t", "rho", "beta", "gamma"}
 # constructor constants of the reference classes that callers read through get_attr

@@ -53,7 +53,10 @@ typedef enum cl_env_kind {
   CL_ENV_LORENZ_RK4 = 7,     /* f64 */
   CL_ENV_LORENZ_RK4_F32 = 8, /* f32 */
   CL_ENV_PMSM_RK4 = 9,       /* f64 PMSM pair, per-env sigma/gamma */
-  CL_ENV_KIND_COUNT = 10
+  /* further parity kinds */
+  CL_ENV_MEMRISTIVE4_PAIR = 10, /* lorenz_env_transient2.py  4-D memristive pair, u*100 control */
+  CL_ENV_PMSM_FREE = 11,        /* lorenz_singlecontrol.py   uncontrolled noisy PMSM, fixed IC  */
+  CL_ENV_KIND_COUNT = 12
 } cl_env_kind;
 
 /* ---- flags ------------------------------------------------------------------------ */
@@ -248,6 +251,41 @@ int64_t cl_launch_count(const cl_ctx* ctx);
 int cl_block_size(const cl_ctx* ctx);
 /* cl_rollout calls served by the dynamically scheduled kernel (env-warp x interval-chunk tasks) */
 int64_t cl_dyn_launch_count(const cl_ctx* ctx);
+
+/* -- device-side SB3 plumbing that directly follows the env step; all
+ *    pointers are DEVICE pointers, calls only enqueue on `stream` of the current device. */
+
+/* GAE(lambda): stable_baselines3 2.7.1 RolloutBuffer.compute_returns_and_advantage (un-vendored;
+ * driven by code/train.py:112-120).  Time-major float32 planes [T][stride], n <= stride envs;
+ * episode_starts[t] = 1 where env i started a new episode at step t; last_dones f32 [n]. */
+int cl_gae(void* stream, const float* rewards, const float* values, const float* episode_starts,
+           const float* last_values, const float* last_dones, double gamma, double gae_lambda,
+           int32_t T, int64_t n, int64_t stride, float* advantages, float* returns);
+
+/* VecNormalize (code/lorenz_pmsm/train.py:118,170; SB3 RunningMeanStd + normalize_obs):
+ * cl_obs_moments: out2d[0..dim) = sum_i (x_ic - shift_c), out2d[dim..2dim) = sum_i (x_ic - shift_c)^2
+ * over the n envs (f64); cl_obs_normalize: out = clip((x - mean)/sqrt(var + eps), +-clip) as f32.
+ * obs addressed obs[i*es + c*cs] like cl_io. */
+int cl_obs_moments(void* stream, const float* obs, int64_t es, int64_t cs, int64_t n, int32_t dim,
+                   const double* shift, double* out2d);
+int cl_obs_normalize(void* stream, const float* in, int64_t ies, int64_t ics, float* out, int64_t oes,
+                     int64_t ocs, int64_t n, int32_t dim, const double* mean, const double* var,
+                     double epsilon, double clip);
+
+/* VecFrameStack (code/lorenz_filter/train.py:115; SB3 StackedObservations for 1-D observations):
+ * stacked f32 [n][dim*n_stack] row-major is rolled by one frame, zeroed where done, then the new
+ * observation is written into the last frame. */
+int cl_frame_stack(void* stream, float* stacked, const float* obs, int64_t es, int64_t cs,
+                   const uint8_t* done, int64_t n, int32_t dim, int32_t n_stack);
+
+/* Evaluation metrics of code/lorenz_pmsm/test_evaluate.py:25-59,239-250 for n trajectories at once:
+ * err f64 [T][n_err][stride], ctrl f64 [T][n_ctrl][stride] -> out4 f64 [n][4] =
+ * (MAE, RMSE over steps >= steady_start averaged over components; settling time = (last step
+ * with |e| > error_band, any component) + 1) * dt, NaN if a component never settles... see
+ * calculate_advanced_metrics; control energy sum(u^2) * dt). */
+int cl_eval_metrics(void* stream, const double* err, const double* ctrl, int32_t T, int32_t n_err,
+                    int32_t n_ctrl, int64_t n, int64_t stride, int32_t steady_start, double dt,
+                    double error_band, double* out4);
 
 /* -- host-side test hooks (no GPU needed): the exact Philox block and uniform mapping
  *    the kernels use, compiled from the same source. */

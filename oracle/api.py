@@ -18,6 +18,7 @@ LIB = os.path.join(HERE, "libchaos_oracle.so")
 KINDS = {
     "lorenz3": 0, "lorenz3_pair": 1, "lorenz4_pair": 2, "hr_sync": 3, "pmsm_sync": 4,
     "pmsm_classic": 5, "pmsm_single": 6, "lorenz_rk4": 7, "lorenz_rk4_f32": 8, "pmsm_rk4": 9,
+    "memristive4_pair": 10, "pmsm_free": 11,
 }
 F_ADD_NOISE, F_EVAL_MODE, F_ADD_FILTER, F_AUTORESET = 1, 2, 4, 8
 

@@ -28,7 +28,8 @@
 
 enum {
   K_LORENZ3 = 0, K_LORENZ3_PAIR = 1, K_LORENZ4_PAIR = 2, K_HR_SYNC = 3, K_PMSM_SYNC = 4,
-  K_PMSM_CLASSIC = 5, K_PMSM_SINGLE = 6, K_LORENZ_RK4 = 7, K_LORENZ_RK4_F32 = 8, K_PMSM_RK4 = 9
+  K_PMSM_CLASSIC = 5, K_PMSM_SINGLE = 6, K_LORENZ_RK4 = 7, K_LORENZ_RK4_F32 = 8, K_PMSM_RK4 = 9,
+  K_MEMRISTIVE4_PAIR = 10, K_PMSM_FREE = 11
 };
 enum { F_ADD_NOISE = 1, F_EVAL_MODE = 2, F_ADD_FILTER = 4, F_AUTORESET = 8 };
 enum { DONE_TERM = 1, DONE_TRUNC = 2 };
@@ -120,6 +121,14 @@ static void pmsm64_rhs(const double* s, double* d) {
   d[1] = -s[1] - s[0] * s[2] + b * s[2];
   d[2] = a * (s[1] - s[2]);
 }
+/* lorenz_env_transient2.py step/reset right-hand side (a=30, b=1, c=36, d=0.5, h=0.003) */
+static void memristive4_rhs(const double* s, double* d) {
+  const double a = 30.0, b = 1.0, c = 36.0, dd = 0.5, h = 0.003;
+  d[0] = a * (2 * s[3] * s[3] * (s[1] - s[0]) + dd * s[0]);
+  d[1] = b * (2 * s[3] * s[3] * (s[0] - s[1]) - s[2]);
+  d[2] = c * (s[1] - h * s[2]);
+  d[3] = s[1] - s[0] - 0.01 * s[3];
+}
 /* hr_derivatives, lorenz_env_try.py:7-12 (x1**3 and x1**2 are libm pow in NumPy scalars) */
 static void hr_rhs(const double* s, double a1, double a2, double* d) {
   const double a = 1.0, b = 3.0, c = 1.0, dd = 5.0, r = 0.006, sp = 4.0, I = 3.2, xr = -1.6;
@@ -199,9 +208,9 @@ static void rk4_sub_f(const float* q, float* s, const float* u, float h, int S) 
 }
 
 /* ---- per-kind geometry -------------------------------------------------------------------- */
-static const int kNState[10] = {4, 10, 9, 9, 9, 7, 4, 6, 6, 8};
-static const int kObs[10] = {6, 6, 8, 6, 6, 6, 6, 6, 6, 6};
-static const int kAct[10] = {3, 3, 3, 2, 2, 2, 2, 3, 3, 2};
+static const int kNState[12] = {4, 10, 9, 9, 9, 7, 4, 6, 6, 8, 9, 4};
+static const int kObs[12] = {6, 6, 8, 6, 6, 6, 6, 6, 6, 6, 8, 6};
+static const int kAct[12] = {3, 3, 3, 2, 2, 2, 2, 3, 3, 2, 3, 2};
 static int is_f32(int kind) { return kind == K_PMSM_SYNC || kind == K_LORENZ_RK4_F32; }
 
 int orc_n_state(int kind) { return kNState[kind]; }
@@ -214,7 +223,8 @@ typedef struct { double x[12]; int32_t adam; } env_t;
 static int env_finite(int kind, const env_t* e) {
   double s = 0;
   int n = (kind == K_LORENZ3 || kind == K_LORENZ3_PAIR || kind == K_PMSM_SINGLE || kind == K_LORENZ_RK4 ||
-           kind == K_LORENZ_RK4_F32) ? 3 : (kind == K_LORENZ4_PAIR ? 8 : 6);
+           kind == K_LORENZ_RK4_F32 || kind == K_PMSM_FREE) ? 3
+          : ((kind == K_LORENZ4_PAIR || kind == K_MEMRISTIVE4_PAIR) ? 8 : 6);
   for (int c = 0; c < n; ++c) s += e->x[c];
   return isfinite(s);
 }
@@ -239,9 +249,13 @@ static void observe(int kind, const env_t* e, double* obs) {
       pmsm64_rhs(e->x, d); pmsm64_rhs(e->x + 3, d2);
       for (int c = 0; c < 3; ++c) { obs[c] = e->x[c] - e->x[3 + c]; obs[3 + c] = d[c] - d2[c]; }
       break;
-    case K_PMSM_SINGLE:
+    case K_PMSM_SINGLE: case K_PMSM_FREE:
       pmsm64_rhs(e->x, d);
       for (int c = 0; c < 3; ++c) { obs[c] = e->x[c]; obs[3 + c] = d[c]; }
+      break;
+    case K_MEMRISTIVE4_PAIR:
+      memristive4_rhs(e->x, d); memristive4_rhs(e->x + 4, d2);
+      for (int c = 0; c < 4; ++c) { obs[c] = e->x[c] - e->x[4 + c]; obs[4 + c] = d[c] - d2[c]; }
       break;
     case K_LORENZ_RK4: {
       const double z[3] = {0, 0, 0};
@@ -283,6 +297,11 @@ static void env_reset(const orc_cfg* cfg, env_t* e, const rng_t* rng, double* ob
       observe(cfg->kind, e, obs);
       break;
     }
+    case K_PMSM_FREE:  /* lorenz_singlecontrol.py reset: fixed initial condition, no draw */
+      e->x[0] = 25.0; e->x[1] = 1.0; e->x[2] = -1.0; e->x[3] = 0.0;
+      observe(cfg->kind, e, obs);
+      break;
+    case K_MEMRISTIVE4_PAIR:  /* lorenz_env_transient2.py reset */
     case K_LORENZ4_PAIR:  /* lorenz_env_transient.py:275-297 */
       draw_uniform(rng, TAG_RESET, 8, 0.0, 5.0, u);
       for (int c = 0; c < 8; ++c) e->x[c] = u[c];
@@ -443,6 +462,33 @@ static void env_step(const orc_cfg* cfg, env_t* e, const float* a, const double*
       term = (e->x[3] == 10.0);
       break;
     }
+    case K_MEMRISTIVE4_PAIR: {  /* lorenz_env_transient2.py step */
+      float u1 = clipf(a[0], -2.0f, 2.0f) * 100.0f, u2 = clipf(a[1], -2.0f, 2.0f) * 100.0f,
+            u3 = clipf(a[2], -2.0f, 2.0f) * 100.0f;
+      memristive4_rhs(e->x, d);
+      for (int c = 0; c < 4; ++c) e->x[c] = e->x[c] + d[c] * 0.001;
+      memristive4_rhs(e->x + 4, d);
+      d[0] = d[0] + (double)u1; d[1] = d[1] + (double)u2; d[3] = d[3] + (double)u3;
+      for (int c = 0; c < 4; ++c) e->x[4 + c] = e->x[4 + c] + d[c] * 0.001;
+      observe(cfg->kind, e, obs);
+      double E = 0.0; for (int c = 0; c < 4; ++c) E = E + fabs(obs[c]);
+      rew = -E - pow(E, 1.0 / 3);
+      e->x[8] = e->x[8] + 0.001;
+      term = (e->x[8] == 5.0) || (rew < -1e6);
+      break;
+    }
+    case K_PMSM_FREE: {  /* lorenz_singlecontrol.py step (takes no action) */
+      double n0 = 0.0 + 3.0 * nz[0], n1 = 0.0 + 3.0 * nz[1], n2 = 0.0 + 3.0 * nz[2];
+      pmsm64_rhs(e->x, d);
+      d[0] = d[0] + n0; d[1] = d[1] + n1; d[2] = d[2] + n2;
+      for (int c = 0; c < 3; ++c) e->x[c] = e->x[c] + d[c] * 0.01;
+      observe(cfg->kind, e, obs);
+      rew = 0.0; for (int c = 0; c < 3; ++c) rew = rew + fabs(obs[c]);
+      rew = -rew;
+      e->x[3] = e->x[3] + 0.01;
+      term = (e->x[3] == 1000.0);
+      break;
+    }
     case K_LORENZ_RK4: {
       const float lim = (float)cfg->act_limit;
       double u[3];
@@ -567,7 +613,7 @@ void orc_rollout(const orc_cfg* cfg, int T, double synth_amp, void* state, int32
           for (int c = 0; c < na; ++c) a[c] = (float)synth_amp * (2.0f * ((float)(w[c] >> 8) * (1.0f / 16777216.0f)) - 1.0f);
         }
         double nz[4] = {0, 0, 0, 0};
-        int want = (kind == K_PMSM_CLASSIC) || ((kind == K_HR_SYNC || kind == K_PMSM_SYNC) && (cfg->flags & F_ADD_NOISE));
+        int want = (kind == K_PMSM_CLASSIC) || (kind == K_PMSM_FREE) || ((kind == K_HR_SYNC || kind == K_PMSM_SYNC) && (cfg->flags & F_ADD_NOISE));
         if (want) {
           if (noise) for (int c = 0; c < 3; ++c) nz[c] = noise[(int64_t)c * np_ + i];
           else draw_normal(&rng, TAG_NOISE, 3, nz);

@@ -144,3 +144,13 @@ def pmsm_classic():
 def pmsm_single():
     """lorenz_env_transient1.py::lorenzEnv_transient (single PMSM to the origin)."""
     return load("lorenz_env_transient1.py").lorenzEnv_transient()
+
+
+def memristive4_pair():
+    """lorenz_env_transient2.py::lorenzEnv_transient (4-D memristive pair, u*100 control)."""
+    return load("lorenz_env_transient2.py").lorenzEnv_transient()
+
+
+def pmsm_free():
+    """lorenz_singlecontrol.py::lorenzEnv_transient (uncontrolled noisy PMSM; step() has no action)."""
+    return load("lorenz_singlecontrol.py").lorenzEnv_transient()

@@ -49,9 +49,12 @@ CASES = [
     ("pmsm_sync_diverge", "pmsm_sync", 9, 2, {"alpha": 0.5}, (-600, 600), 1.0),
     ("pmsm_classic", "pmsm_classic", 7, 2, {}, (-10, 10), 2.5),
     ("pmsm_single", "pmsm_single", 4, 2, {}, (-20, 20), 0.5),
+    ("memristive4_pair", "memristive4_pair", 9, 3, {}, (0, 5), 2.5),
+    ("pmsm_free", "pmsm_free", 4, 2, {}, (-20, 20), 0.0),
 ]
 ZERO_PLANES = {
     "lorenz3": [3], "lorenz3_pair": [3], "lorenz4_pair": [8], "pmsm_classic": [6], "pmsm_single": [3],
+    "memristive4_pair": [8], "pmsm_free": [3],
 }
 
 

@@ -11,7 +11,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PARITY_CASES = [
     "lorenz3", "lorenz3_pair", "lorenz4_pair", "hr_sync", "hr_sync_filter", "hr_sync_noise",
     "hr_sync_diverge", "pmsm_sync_a050", "pmsm_sync_a033_noise", "pmsm_sync_diverge",
-    "pmsm_classic", "pmsm_single",
+    "pmsm_classic", "pmsm_single", "memristive4_pair", "pmsm_free",
 ]
 # Per-interval tolerances.  f64 kinds: the north_star bar (1e-12 relative).  PMSM_SYNC is a
 # float32 env: states are pure f32 mul/add (bit-exact); reward / lambda / v_t go through

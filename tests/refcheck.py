@@ -32,14 +32,19 @@ def make_reference(kind, **kw):
     return {
         "lorenz3": R.lorenz3, "lorenz3_pair": R.lorenz3_pair, "lorenz4_pair": R.lorenz4_pair,
         "hr_sync": R.hr_sync, "pmsm_sync": R.pmsm_sync, "pmsm_classic": R.pmsm_classic,
-        "pmsm_single": R.pmsm_single,
+        "pmsm_single": R.pmsm_single, "memristive4_pair": R.memristive4_pair, "pmsm_free": R.pmsm_free,
     }[kind](**kw)
 
 
 def inject(kind, env, st):
     """Put oracle-layout state vector `st` (one env, plane order of the C-ABI) into `env`."""
     st = np.asarray(st)
-    if kind in ("lorenz3", "pmsm_single"):
+    if kind == "pmsm_free":
+        env.state1 = [float(v) for v in st[:3]]   # a Python list in the reference
+        env.state2 = np.array([0, 0, 0, 0, 0, 0])
+        env.t = float(st[3])
+        env.state0 = [0.0] * 6
+    elif kind in ("lorenz3", "pmsm_single"):
         env.state1 = np.array(st[:3], np.float64)
         env.state2 = np.array([0, 0, 0, 0, 0, 0])
         env.t = float(st[3])
@@ -50,9 +55,11 @@ def inject(kind, env, st):
         env.state2 = [float(v) for v in st[4:10]]
         env.state12 = np.array(st[4:7], np.float64)
         env.state0 = [0.0] * 6
-    elif kind == "lorenz4_pair":
+    elif kind in ("lorenz4_pair", "memristive4_pair"):
         env.state1 = np.array(st[:4], np.float64)
-        env.state2 = [float(v) for v in st[4:8]] + [0.0] * 4  # 8-list after reset()/step()
+        # 8-list of np.float64 scalars after reset()/step() (Python floats would turn
+        # `float + np.float32` into float32 under NEP 50 -- not what the reference holds)
+        env.state2 = [np.float64(v) for v in st[4:8]] + [np.float64(0.0)] * 4
         env.t = float(st[8])
         env.state0 = [0.0] * 8
     elif kind == "hr_sync":
@@ -76,11 +83,11 @@ def inject(kind, env, st):
 
 
 def extract(kind, env):
-    if kind in ("lorenz3", "pmsm_single"):
+    if kind in ("lorenz3", "pmsm_single", "pmsm_free"):
         return np.array([*env.state1[:3], env.t], np.float64)
     if kind == "lorenz3_pair":
         return np.array([*env.state1[:3], env.t, *env.state2[:6]], np.float64)
-    if kind == "lorenz4_pair":
+    if kind in ("lorenz4_pair", "memristive4_pair"):
         return np.array([*env.state1[:4], *env.state2[:4], env.t], np.float64)
     if kind == "hr_sync":
         return np.array([*env.state_master, *env.state_slave, env.sigma, *env.filtered_action], np.float64)
@@ -95,7 +102,7 @@ NOISY = {"pmsm_classic": True}
 
 
 def uses_noise(kind, kw):
-    return kind == "pmsm_classic" or (kind in ("hr_sync", "pmsm_sync") and kw.get("add_noise", False))
+    return kind in ("pmsm_classic", "pmsm_free") or (kind in ("hr_sync", "pmsm_sync") and kw.get("add_noise", False))
 
 
 def drive_reference(kind, st0, actions, noise=None, adam_step=0, cur_step=0, **kw):
@@ -118,7 +125,12 @@ def drive_reference(kind, st0, actions, noise=None, adam_step=0, cur_step=0, **k
     states, obs, rew, done = [], [], [], []
     try:
         for t in range(T):
-            out = env.step(np.asarray(actions[t], np.float32))
+            if kind == "pmsm_free":
+                import contextlib, io
+                with contextlib.redirect_stdout(io.StringIO()):  # the reference prints while t <= 1
+                    out = env.step()
+            else:
+                out = env.step(np.asarray(actions[t], np.float32))
             if len(out) == 4:
                 o, r, d, _ = out
                 flag = 1 if d else 0

@@ -14,7 +14,7 @@ import helpers as H
 
 pytestmark = pytest.mark.gpu
 
-EULER_EXACT = {"lorenz3", "lorenz3_pair", "lorenz4_pair", "pmsm_single"}  # pure IEEE mul/add kinds
+EULER_EXACT = {"lorenz3", "lorenz3_pair", "lorenz4_pair", "pmsm_single", "pmsm_free"}  # pure IEEE mul/add kinds
 
 
 @pytest.mark.parametrize("name", H.PARITY_CASES)
@@ -102,7 +102,7 @@ def test_pmsm_xlsx_float32_kats_on_gpu():
     ("lorenz3", {}, 0.05), ("lorenz3_pair", {}, 0.05), ("lorenz4_pair", {}, 1.0),
     ("hr_sync", {}, 1.0), ("hr_sync", {"add_filter": True, "add_noise": True}, 1.0),
     ("pmsm_sync", {"alpha": 0.25}, 1.0), ("pmsm_sync", {"alpha": 0.5, "add_noise": True}, 1.0),
-    ("pmsm_classic", {}, 2.0), ("pmsm_single", {}, 0.5),
+    ("pmsm_classic", {}, 2.0), ("pmsm_single", {}, 0.5), ("memristive4_pair", {}, 2.0), ("pmsm_free", {}, 0.0),
 ])
 def test_gpu_vs_oracle_seeded_batch_with_autoreset(oracle_api, kind, kw, amp):
     """4096 envs x 40 steps free-running, Philox resets + Philox noise on both sides, TimeLimit

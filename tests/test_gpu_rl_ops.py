@@ -1,0 +1,171 @@
+"""Device RL plumbing (csrc/tu_rl_ops.cu) against the NumPy restatements of SB3 / the reference's
+metric functions (oracle/sb3_ref.py)."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import sb3_ref as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("T,N", [(128, 4096), (2048, 33), (16, 65536)])
+def test_gae_bit_exact_vs_sb3_restatement(T, N):
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    rng = np.random.default_rng(T)
+    r = rng.normal(size=(T, N)).astype(np.float32)
+    v = rng.normal(size=(T, N)).astype(np.float32)
+    starts = (rng.random((T, N)) < 0.02).astype(np.float32)
+    lv = rng.normal(size=N).astype(np.float32)
+    dones = (rng.random(N) < 0.1).astype(np.float32)
+    adv_ref, ret_ref = S.gae(r, v, starts, lv, dones, 0.99, 0.95)
+    dev = "cuda:0"
+    adv, ret = rl_ops.gae(*(torch.as_tensor(x, device=dev) for x in (r, v, starts, lv, dones)), 0.99, 0.95)
+    assert np.array_equal(adv.cpu().numpy(), adv_ref)
+    assert np.array_equal(ret.cpu().numpy(), ret_ref)
+
+
+def test_running_moments_and_normalize():
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    rng = np.random.default_rng(3)
+    dev = torch.device("cuda:0")
+    rms_d = rl_ops.RunningMeanStd((6,), dev)
+    rms_o = S.RunningMeanStd(shape=(6,))
+    for k in range(5):
+        x = (rng.normal(2.0 * k, 1.0 + k, size=(8192, 6))).astype(np.float32)
+        rms_d.update(torch.as_tensor(x, device=dev))
+        rms_o.update(x)
+        assert np.allclose(rms_d.mean.cpu().numpy(), rms_o.mean, rtol=2e-6, atol=1e-6)
+        assert np.allclose(rms_d.var.cpu().numpy(), rms_o.var, rtol=2e-5)
+        assert np.isclose(rms_d.count, rms_o.count)
+    # normalisation itself is exact given the same statistics (float64 math, one rounding to f32)
+    class V:  # minimal venv stand-in
+        num_envs = 8192
+        class batch:
+            obs_dim, device = 6, dev
+    vn = rl_ops.DeviceVecNormalize(V, clip_obs=2.0)
+    vn.obs_rms = rms_d
+    z = vn.normalize_obs(torch.as_tensor(x, device=dev)).cpu().numpy()
+    rms_same = S.RunningMeanStd(shape=(6,))
+    rms_same.mean, rms_same.var = rms_d.mean.cpu().numpy(), rms_d.var.cpu().numpy()
+    assert np.array_equal(z, S.normalize_obs(x, rms_same, clip_obs=2.0))
+    # SoA (strided) input view gives the same result
+    xs = torch.as_tensor(np.ascontiguousarray(x.T), device=dev).t()
+    assert np.array_equal(vn.normalize_obs(xs).cpu().numpy(), z)
+
+
+def test_frame_stack_exact():
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    rng = np.random.default_rng(4)
+    N, dim, k = 5000, 6, 4
+    dev = torch.device("cuda:0")
+
+    class V:
+        num_envs = N
+        class batch:
+            obs_dim, device = dim, dev
+    fs = rl_ops.DeviceVecFrameStack(V, k)
+    ref = np.zeros((N, dim * k), np.float32)
+    for t in range(9):
+        obs = rng.normal(size=(N, dim)).astype(np.float32)
+        done = (rng.random(N) < 0.2).astype(np.uint8)
+        out = fs._push(torch.as_tensor(obs, device=dev), torch.as_tensor(done, device=dev))
+        ref = S.frame_stack_update(ref, obs, done)
+        assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_eval_metrics_vs_reference_functions():
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    rng = np.random.default_rng(5)
+    T, N = 2400, 64
+    t = np.arange(T)[:, None, None]
+    tau = rng.uniform(20, 400, size=(1, 3, N))
+    e = rng.uniform(0.5, 30, size=(1, 3, N)) * np.exp(-t / tau) * np.cos(t / 7.0) + 0.01 * rng.normal(size=(T, 3, N))
+    e[-1, 0, 0] = 1.0          # env 0: component 0 never settles
+    e[-1, :, 1] = 1.0          # env 1: nothing settles -> NaN
+    e[:, :, 2] = 0.001         # env 2: never leaves the band -> 0
+    u = rng.normal(size=(T, 2, N)) * 50
+    out = rl_ops.eval_metrics(torch.as_tensor(e, device="cuda:0"), torch.as_tensor(u, device="cuda:0"), dt=0.001)
+    for i in range(N):
+        mae, rmse, ts, en = S.steady_state_metrics(e[:, :, i], u[:, :, i], dt=0.001)
+        assert np.isclose(out["mae"][i].item(), mae, rtol=1e-12)
+        assert np.isclose(out["rmse"][i].item(), rmse, rtol=1e-12)
+        assert np.isclose(out["energy"][i].item(), en, rtol=1e-12)
+        got = out["settling_time"][i].item()
+        assert (np.isnan(ts) and np.isnan(got)) or got == ts, (i, got, ts)
+    assert np.isnan(out["settling_time"][1].item()) and out["settling_time"][2].item() == 0.0
+
+
+def test_device_vecnormalize_framestack_on_real_env():
+    """PMSM pipeline of code/lorenz_pmsm/train.py:166-170 (VecNormalize, clip_obs=10) and the
+    filter pipeline of code/lorenz_filter/train.py:115 (VecFrameStack 4) on the tensor path."""
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n = 4096
+    env = BatchedChaosVecEnv("pmsm_sync", n, alpha=0.5, seed=2, max_episode_steps=7)
+    vn = rl_ops.DeviceVecNormalize(env, norm_obs=True, norm_reward=False, clip_obs=10.0)
+    fs = rl_ops.DeviceVecFrameStack(vn, 4)
+    rms = S.RunningMeanStd(shape=(6,))
+    stack = np.zeros((n, 24), np.float32)
+    obs = fs.reset_tensor()
+    raw = vn.get_original_obs().cpu().numpy()
+    rms.update(raw)
+    stack = S.frame_stack_update(stack, S.normalize_obs(raw, rms), np.zeros(n, bool))
+    assert np.allclose(obs.cpu().numpy(), stack, rtol=1e-5, atol=1e-5)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for t in range(10):
+        a = (torch.rand((n, 2), generator=g) * 2 - 1).to("cuda:0")
+        obs, rew, done = fs.step_tensor(a)
+        raw = vn.get_original_obs().cpu().numpy()
+        rms.update(raw)
+        stack = S.frame_stack_update(stack, S.normalize_obs(raw, rms), done.cpu().numpy() != 0)
+        assert np.allclose(obs.cpu().numpy(), stack, rtol=2e-5, atol=2e-5), t
+        assert rew.dtype == torch.float32
+    assert np.allclose(vn.obs_rms.mean.cpu().numpy(), rms.mean, rtol=1e-5, atol=1e-5)
+    env.close()
+
+
+def test_device_rollout_collector_matches_sb3_bookkeeping():
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n, T = 2048, 24
+    env = BatchedChaosVecEnv("hr_sync", n, seed=5, max_episode_steps=10)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.Tanh(), torch.nn.Linear(32, 3)).to("cuda:0")
+
+    def policy(obs):
+        y = net(obs)
+        return torch.tanh(y[:, :2]), y[:, 2], -0.5 * (y[:, :2] ** 2).sum(1)
+
+    col = rl_ops.DeviceRolloutCollector(env, policy, n_steps=T, gamma=0.99, gae_lambda=0.95)
+    out = col.collect()
+    for k in ("obs", "actions", "rewards", "values", "log_probs", "episode_starts", "advantages", "returns"):
+        assert out[k].is_cuda and out[k].shape[0] == T
+    starts = out["episode_starts"].cpu().numpy()
+    assert starts[0].all()                                   # SB3: _last_episode_starts = ones at the start
+    assert starts[10].all() and starts[20].all() and not starts[5].any()   # TimeLimit 10, no early termination expected
+    # GAE of the collected buffers equals the SB3 restatement bit-for-bit
+    with torch.no_grad():
+        lv = policy(col._last_obs)[1].cpu().numpy()
+    adv, ret = S.gae(out["rewards"].cpu().numpy(), out["values"].cpu().numpy(), starts, lv,
+                     col._last_starts.cpu().numpy(), 0.99, 0.95)
+    assert np.array_equal(out["advantages"].cpu().numpy(), adv)
+    assert np.array_equal(out["returns"].cpu().numpy(), ret)
+    # the truncated step's reward carries the bootstrap gamma * V(terminal_obs)
+    env2 = BatchedChaosVecEnv("hr_sync", n, seed=5, max_episode_steps=10)
+    obs = env2.reset_tensor().clone()
+    with torch.no_grad():
+        for t in range(10):
+            a, _, _ = policy(obs)
+            o, r, d = env2.step_tensor(a)
+            raw_r = r.float().clone()
+            obs = o.clone()
+        tv = policy(env2.batch.terminal_obs())[1]
+    assert torch.allclose(out["rewards"][9], raw_r + 0.99 * tv, rtol=1e-6, atol=1e-6)
+    env.close(); env2.close()
