@@ -40,6 +40,12 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 FLOP_PER_SUBSTEP = 87          # Lorenz RK4 substep with 3-channel ZOH control
 BYTES_PER_ENV_STEP = 12 + 24 + 8 + 1   # action f32x3 in; obs f32x6, reward f64, done u8 out
+# per kind: (algorithmic flop per substep, bytes per env-step in the rollout streams, dtype, FMA width)
+KIND_INFO = {
+    "lorenz_rk4": (87, 12 + 24 + 8 + 1, "f64", 8),
+    "lorenz_rk4_f32": (87, 12 + 24 + 4 + 1, "f32", 4),
+    "pmsm_rk4": (2 * 91, 8 + 24 + 8 + 1, "f64", 8),     # master + slave, 91 flop each
+}
 
 
 def parse():
@@ -60,8 +66,9 @@ def parse():
 
 def workload_config(args, world):
     return {
-        "workload": f"Lorenz targeting env (RK4 x {args.substeps} substeps, dt=0.01, FP64), "
-                    f"{args.envs_per_gpu} envs/GPU, random actions (BASELINE.json configs[1])",
+        "workload": (f"Lorenz targeting env (RK4 x {args.substeps} substeps, dt=0.01, FP64), "
+                     f"{args.envs_per_gpu} envs/GPU, random actions (BASELINE.json configs[1])")
+        if args.kind == "lorenz_rk4" else f"{args.kind} (RK4 x {args.substeps}), {args.envs_per_gpu} envs/GPU, random actions",
         "kind": args.kind, "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
         "substeps": args.substeps, "control_intervals_per_step": args.chunk,
         "parallelism": f"env-slab x{world} (no data-path collective; 64 B stats all-reduce per step)",
@@ -129,8 +136,8 @@ def cpu_arm(args, budget_s):
     n = args.envs_per_gpu
     threads = len(os.sched_getaffinity(0))   # all host cores, whatever OMP_NUM_THREADS torchrun exported
     O.set_threads(threads)
-    orc = O.Oracle(args.kind, n, flags=O.F_AUTORESET, seed=0, substeps=args.substeps, dt=0.01,
-                   act_limit=1.0, act_gain=50.0, max_episode_steps=1000)
+    orc = O.Oracle(args.kind, n, flags=O.F_AUTORESET, seed=0, substeps=args.substeps,
+                   dt=0.001 if args.kind == "pmsm_rk4" else 0.01, act_limit=1.0, act_gain=50.0, max_episode_steps=1000)
     orc.reset()
     t0 = time.perf_counter(); orc.rollout_timed(1); dt1 = time.perf_counter() - t0   # also warms up
     T = max(1, min(4096, int(budget_s / max(dt1, 1e-6))))
@@ -195,9 +202,11 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     slab = D.weak_slab(args.envs_per_gpu, world, rank)
     N, T, S = slab.num_envs, args.chunk, args.substeps
+    flop_sub, bytes_step, dtype_name, fma_bytes = KIND_INFO[args.kind]
 
+    env_dt = 0.001 if args.kind == "pmsm_rk4" else 0.01
     batch = ChaosBatch(args.kind, N, device=dev, seed=0, env_id_base=slab.env_id_base, substeps=S,
-                       dt=0.01, autoreset=True, max_episode_steps=1000)
+                       dt=env_dt, autoreset=True, max_episode_steps=1000)
     batch.reset()
     NP = batch.n_pad
     # synthetic random actions, SoA time-major, resident in HBM before the timed region
@@ -205,7 +214,7 @@ def run_b200(args):
     act_soa = torch.rand((T, batch.act_dim, NP), generator=g, device=dev, dtype=torch.float32) * 2 - 1
     actions = act_soa[:, :, :N].permute(0, 2, 1)       # [T, N, A] view, env stride 1
     out = {"obs": torch.empty((T, batch.obs_dim, NP), dtype=torch.float32, device=dev),
-           "reward": torch.empty((T, NP), dtype=torch.float64, device=dev),
+           "reward": torch.empty((T, NP), dtype=batch.real, device=dev),
            "done": torch.empty((T, NP), dtype=torch.uint8, device=dev)}
     side = torch.cuda.Stream(device=dev)
 
@@ -265,37 +274,37 @@ def run_b200(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-        fp64_peak = measure_fma_peak(local, 8, 0.5)
-        flops = float(N) * T * S * FLOP_PER_SUBSTEP
+        fp64_peak = measure_fma_peak(local, fma_bytes, 0.5)
+        flops = float(N) * T * S * flop_sub
         ach = flops / (kern_ms * 1e-3) * 1e-12
-        gbs = float(N) * T * BYTES_PER_ENV_STEP / (kern_ms * 1e-3) * 1e-9
+        gbs = float(N) * T * bytes_step / (kern_ms * 1e-3) * 1e-9
         dyn = batch.dyn_launch_count > 0
         traffic = None
         try:   # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             w = tj["workload"]
             if (w["kind"], w["envs"], w["chunk"], w["substeps"]) == (args.kind, N, T, S) and dyn:
-                traffic = {"bytes": tj["dram_bytes_read"] + tj["dram_bytes_write"], "algorithmic_bytes": int(N) * T * BYTES_PER_ENV_STEP,
+                traffic = {"bytes": tj["dram_bytes_read"] + tj["dram_bytes_write"], "algorithmic_bytes": int(N) * T * bytes_step,
                            "source": tj["source"]}
         except Exception:  # noqa: BLE001
             pass
         roofline = {
             "kernel": ("cl::k_rollout_dyn<EnvLorenzRK4<double>> (fused T-interval rollout, env-warp x chunk tasks)" if dyn
                        else "cl::k_step<EnvLorenzRK4<double>, ROLL=true> (fused T-interval rollout)"),
-            "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+            "bound": "fp64" if fma_bytes == 8 else "fp32", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": ach / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
             "peak_source": "DFMA-chain micro-kernel (cl_measure_fma_peak) run in this process, 2 flop/FMA; "
                            "MEASURED_PEAKS.json has no FP64 entry",
-            "algorithmic_flop_per_substep": FLOP_PER_SUBSTEP,
+            "algorithmic_flop_per_substep": flop_sub,
             "fma_issue_ceiling": 87.0 / (2 * 49),
             "kernel_ms_per_launch": kern_ms,
             "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                    "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": hbm_src},
+                    "bytes_per_env_step": bytes_step, "peak_source": hbm_src},
         }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_all / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype_name, "data": "synthetic",
             "config": workload_config(args, world), "substeps_per_s": value * S,
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
             "block_size": batch.block_size,
@@ -305,7 +314,7 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         env = BatchedChaosVecEnv(args.kind, N, device=dev, seed=0, env_id_base=slab.env_id_base,
-                                 substeps=S, dt=0.01, max_episode_steps=1000)
+                                 substeps=S, dt=env_dt, max_episode_steps=1000)
         env.reset()
         rng = np.random.default_rng(rank)
         host_actions = [rng.uniform(-1, 1, (N, env.batch.act_dim)).astype(np.float32) for _ in range(8)]

@@ -194,14 +194,18 @@ class BatchedChaosVecEnv(VecEnv):
         if n_done:
             idx = np.flatnonzero(dones)
             now = round(time.time() - self._t_start, 6)
-            for i in idx.tolist():
-                flag = int(done[i])
+            tobs = term_obs[idx]                      # one gather; rows are handed out as views
+            flags = done[idx]
+            trunc = (((flags & L.DONE_TRUNCATED) != 0) & ((flags & L.DONE_TERMINATED) == 0)).tolist()
+            rets, lens, ids = ler[idx].tolist(), lel[idx].tolist(), idx.tolist()
+            monitor = self._monitor
+            for k, i in enumerate(ids):
                 d = infos[i]
-                d["terminal_observation"] = term_obs[i].copy()
-                d["TimeLimit.truncated"] = bool(flag & L.DONE_TRUNCATED) and not bool(flag & L.DONE_TERMINATED)
-                if self._monitor:
-                    d["episode"] = {"r": float(ler[i]), "l": int(lel[i]), "t": now}
-            self._dirty = idx.tolist()
+                d["terminal_observation"] = tobs[k]
+                d["TimeLimit.truncated"] = trunc[k]
+                if monitor:
+                    d["episode"] = {"r": rets[k], "l": lens[k], "t": now}
+            self._dirty = ids
         return obs, rew, dones, infos
 
     def close(self) -> None:

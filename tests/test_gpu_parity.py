@@ -196,3 +196,86 @@ def test_hr_rk4_full_size_vs_oracle(oracle_api):
     frac = np.mean(b.state.cpu().numpy()[:6] == o.state[:6])
     assert frac > 0.99, frac
     b.close()
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 127, 129, 1000])
+@pytest.mark.parametrize("kind,amp", [("lorenz3", 0.05), ("hr_sync", 1.0), ("pmsm_sync", 1.0)])
+def test_ragged_and_tiny_batches_vs_oracle(oracle_api, kind, amp, n):
+    """Edge sizes: single env, partial warps, one-past-a-block; padding lanes stay untouched."""
+    import torch
+    O = oracle_api
+    b = H.gpu_batch(kind, n, seed=3, autoreset=True, max_episode_steps=2)
+    o = O.Oracle(kind, n, flags=O.F_AUTORESET, max_episode_steps=2, seed=3)
+    b.reset(); o.reset()
+    rng = np.random.default_rng(n)
+    rt = H.rtol_for(kind)
+    for t in range(5):
+        a = rng.uniform(-amp, amp, (n, b.act_dim)).astype(np.float32)
+        obs, rew, done = b.step(torch.as_tensor(a, device=b.device))
+        ao = np.zeros((o.act_dim, o.n_pad), np.float32); ao[:, :n] = a.T
+        oo, ro, do, _ = o.step(ao)
+        H.assert_close(b.state.double().cpu().numpy()[:, :n], o.state[:, :n].astype(np.float64), rt, f"state n={n}", atol=1e-300)
+        H.assert_close(rew.double().cpu().numpy(), ro[:n], rt, "reward")
+        assert np.array_equal(done.cpu().numpy(), do[:n])
+    assert float(b.state[:, n:].abs().sum().item()) == 0.0 and int(b.ep_len[n:].sum().item()) == 0
+    b.close()
+
+
+def test_nonfinite_and_out_of_range_actions_follow_np_clip(oracle_api):
+    """np.clip propagates NaN and saturates +-inf (dynamic.py:63-65, lorenz_env_try.py:92-93)."""
+    import torch
+    O = oracle_api
+    specials = np.array([np.nan, np.inf, -np.inf, 1e30, -1e30, 0.0, -0.0, 499.99997, 500.00003], np.float32)
+    for kind in ("lorenz3", "hr_sync", "pmsm_sync", "lorenz4_pair"):
+        n = len(specials)
+        b = H.gpu_batch(kind, n, seed=1, autoreset=False, max_episode_steps=0)
+        o = O.Oracle(kind, n, seed=1)
+        b.reset(); o.reset()
+        a = np.zeros((n, b.act_dim), np.float32); a[:, 0] = specials; a[:, -1] = specials[::-1]
+        obs, rew, done = b.step(torch.as_tensor(a, device=b.device))
+        ao = np.zeros((o.act_dim, o.n_pad), np.float32); ao[:, :n] = a.T
+        with np.errstate(all="ignore"):
+            oo, ro, do, _ = o.step(ao)
+        sg, so = b.state.double().cpu().numpy()[:, :n], o.state[:, :n].astype(np.float64)
+        assert H.same_nonfinite(sg, so), kind
+        H.assert_close(sg, so, H.rtol_for(kind), kind)
+        assert H.same_nonfinite(rew.double().cpu().numpy(), ro[:n])
+        assert np.array_equal(done.cpu().numpy(), do[:n])
+        b.close()
+
+
+def test_invalid_arguments_raise():
+    import torch
+    from gym_lorenz_b200 import ChaosLibError
+    with pytest.raises(ChaosLibError):
+        H.gpu_batch("lorenz3", 0)
+    with pytest.raises(KeyError):
+        H.gpu_batch("no_such_env", 4)
+    b = H.gpu_batch("lorenz3", 8)
+    b.reset()
+    with pytest.raises(ValueError):
+        b.step(torch.zeros((8, 2), device=b.device))
+    with pytest.raises(ValueError):
+        b.rollout(4, torch.zeros((4, 7, 3), device=b.device))
+    b.close()
+
+
+def test_maximum_size_8M_envs_slab_invariance():
+    """BASELINE configs[3] total size on ONE GPU (8 Mi envs, f32 RK4): the batch equals the
+    concatenation of 8 x 1 Mi-env slabs keyed by env_id_base (GPU-count invariance)."""
+    import torch
+    n, parts = 8 * 1048576, 8
+    full = H.gpu_batch("lorenz_rk4_f32", n, seed=11, substeps=4)
+    full.reset()
+    full.rollout(3, want=("reward",))
+    ref_state = full.state[:3].clone()
+    ref_ret = full.ep_return.clone()
+    full.close()
+    for r in (0, 5, 7):
+        m = n // parts
+        s = H.gpu_batch("lorenz_rk4_f32", m, seed=11, substeps=4, env_id_base=r * m)
+        s.reset()
+        s.rollout(3, want=("reward",))
+        assert torch.equal(s.state[:3, :m], ref_state[:, r * m:(r + 1) * m])
+        assert torch.equal(s.ep_return[:m], ref_ret[r * m:(r + 1) * m])
+        s.close()

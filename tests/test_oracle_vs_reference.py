@@ -62,3 +62,24 @@ def test_reference_reset_ranges_match_oracle_reset_ranges(oracle_api):
             orc2 = O.Oracle(kind, 2048, seed=5)
             obs = orc2.reset()
             assert np.array_equal(obs[:, 0], ref_obs)
+
+
+def test_special_action_values_clip_like_the_reference(oracle_api):
+    """NaN propagates through np.clip, +-inf saturates; the oracle's clip must agree."""
+    specials = np.array([np.nan, np.inf, -np.inf, 1e30, -1e30, 0.0, -0.0, 499.99997, 500.00003, 2.0000002], np.float32)
+    rng = np.random.default_rng(3)
+    for kind, ns, na, kw in (("lorenz3", 4, 3, {}), ("hr_sync", 9, 2, {}), ("pmsm_sync", 9, 2, {"alpha": 0.5}),
+                             ("pmsm_classic", 7, 2, {}), ("memristive4_pair", 9, 3, {})):
+        import make_golden as MG
+        case = [c for c in MG.CASES if c[1] == kind][0]
+        st = MG.make_ic(rng, kind, ns, *case[5], kw)
+        acts = np.zeros((len(specials), na), np.float32)
+        acts[:, 0] = specials; acts[:, -1] = specials[::-1]
+        nz = rng.standard_normal((len(specials), 3)) if RC.uses_noise(kind, kw) else None
+        with np.errstate(all="ignore"):
+            r = RC.drive_reference(kind, st, acts, nz, **kw)
+            o = RC.drive_oracle(kind, st, acts, nz, **kw)
+        for key in ("state", "obs", "reward"):
+            assert H.same_nonfinite(o[key], r[key]), (kind, key)
+            assert H.max_rel(o[key], r[key]) == 0.0, (kind, key)
+        assert np.array_equal(o["done"], r["done"])
