@@ -253,6 +253,13 @@ def run_b200(args):
             batch.rollout(T, actions, out=out)
         k1.record()
         torch.cuda.synchronize(dev)
+        # short runs (small --steps): keep the same load running, untimed, until the sampler has
+        # seen >= 0.6 s of it, so that `clocks` describes the GPU under THIS load, not idle
+        t_load = time.perf_counter()
+        while (time.perf_counter() - t_load) < 0.6 and (clk.mark() - m0) < 10:
+            for _ in range(20):
+                batch.rollout(T, actions, out=out)
+            torch.cuda.synchronize(dev)
         m2 = clk.mark()
     kern_ms = k0.elapsed_time(k1) / args.steps
     clocks = clk.summary(m0, max(m2, m0 + 1))

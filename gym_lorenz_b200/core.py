@@ -138,6 +138,11 @@ class ChaosBatch:
     def step_index(self, v: int):
         self.lib.cl_set_step_index(self.ctx, int(v))
 
+    def set_graph_mode(self, enable: bool = True) -> None:
+        """Keep the Philox step index on the device so that step/rollout/reset launches can be
+        captured in a CUDA graph (torch.cuda.graph) and replayed."""
+        L.check(self.lib.cl_set_graph_mode(self.ctx, int(bool(enable))), self.ctx, "cl_set_graph_mode")
+
     def _view(self, planes: torch.Tensor) -> torch.Tensor:
         """[C][n_pad] planes -> zero-copy [N, C] view (strides (1, n_pad))."""
         return planes[:, : self.num_envs].t()

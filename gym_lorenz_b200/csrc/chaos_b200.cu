@@ -77,6 +77,8 @@ struct cl_ctx {
   int bc1_n, bc2_n;
   HostStage hs;
   uint32_t* d_dyn;      // [1 + n_envwarps]: task counter + per-env-warp progress (k_rollout_dyn)
+  uint64_t* d_step;     // graph mode: device-resident Philox step index (+ ticket word behind it)
+  int graph_mode;
   int dyn_bps;          // resident worker blocks per SM (0 = not yet queried)
   int64_t dyn_launches;
 };
@@ -181,6 +183,13 @@ extern "C" int cl_create(const cl_config* cfg, cl_ctx** out) {
       *cnt[k] = n;
     }
   }
+  {  // scratch that must exist before any CUDA-graph capture: dyn queue + device step counter
+    const int64_t W = (cfg->num_envs + 31) / 32;
+    e = cudaMalloc((void**)&ctx->d_dyn, sizeof(uint32_t) * (size_t)(W + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_step, 2 * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_step, 0, 2 * sizeof(uint64_t));
+    if (e != cudaSuccess) { int r = fail(nullptr, CL_ECUDA, "scratch allocation: %s", cudaGetErrorString(e)); free(ctx); return r; }
+  }
   *out = ctx;
   return CL_OK;
 }
@@ -206,6 +215,7 @@ extern "C" int cl_destroy(cl_ctx* ctx) {
   if (ctx->d_bc1) cudaFree(ctx->d_bc1);
   if (ctx->d_bc2) cudaFree(ctx->d_bc2);
   if (ctx->d_dyn) cudaFree(ctx->d_dyn);
+  if (ctx->d_step) cudaFree(ctx->d_step);
   free(ctx);
   return CL_OK;
 }
@@ -219,6 +229,7 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
   p.n = c.num_envs; p.n_pad = c.n_pad; p.env_id_base = c.env_id_base;
   p.k0 = (uint32_t)c.seed; p.k1 = (uint32_t)(c.seed >> 32);
   p.step_index = ctx->step_index;
+  if (ctx->graph_mode) { p.step_ptr = ctx->d_step; p.step_ticket = (uint32_t*)(ctx->d_step + 1); }
   p.max_steps = c.max_episode_steps; p.substeps = c.substeps; p.flags = c.flags;
   p.dt = c.dt; p.alpha = c.alpha; p.act_limit = c.act_limit; p.act_gain = c.act_gain;
   p.param_jitter = c.param_jitter;
@@ -295,6 +306,7 @@ static bool want_dynamic(const cl_ctx* ctx, int T, int chunk) {
   if (T < 2 * chunk) return false;
   if (ov && ov[0] == '1') return true;
   if (W <= nsched) return false;
+  if (W * (int64_t)((T + chunk - 1) / chunk) >= (int64_t)1 << 31) return false;  // task ids are 32-bit
   const double eff = (double)W / (double)(((W + nsched - 1) / nsched) * nsched);
   return eff < 0.95;
 }
@@ -316,7 +328,6 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
   int mode = cl::MODE_ROLLOUT;
   if (want_dynamic(ctx, d->T, chunk)) {
     const int64_t W = (ctx->cfg.num_envs + 31) / 32;
-    if (!ctx->d_dyn) CU(cudaMalloc((void**)&ctx->d_dyn, sizeof(uint32_t) * (size_t)(W + 1)));
     if (!ctx->dyn_bps) {
       int occ = 0;
       cudaError_t e = is_parity(ctx->cfg.kind) ? cl_dyn_occupancy_parity(ctx->cfg.kind, chunk, &occ)
@@ -375,12 +386,37 @@ extern "C" int cl_stats(cl_ctx* ctx, void* stream, const cl_buffers* buf, double
 
 extern "C" int cl_get_step_index(const cl_ctx* ctx, uint64_t* out) {
   if (!ctx || !out) return CL_EINVAL;
+  if (ctx->graph_mode) {  // the device counter is authoritative (graph replays advance only it)
+    if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return CL_ECUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return CL_ECUDA;
+    if (cudaMemcpy(out, ctx->d_step, sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess) return CL_ECUDA;
+    return CL_OK;
+  }
   *out = ctx->step_index;
   return CL_OK;
 }
 extern "C" int cl_set_step_index(cl_ctx* ctx, uint64_t v) {
   if (!ctx) return CL_EINVAL;
   ctx->step_index = v;
+  if (ctx->graph_mode) {
+    if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return CL_ECUDA;
+    if (cudaMemcpy(ctx->d_step, &v, sizeof(uint64_t), cudaMemcpyHostToDevice) != cudaSuccess) return CL_ECUDA;
+  }
+  return CL_OK;
+}
+extern "C" int cl_set_graph_mode(cl_ctx* ctx, int enable) {
+  if (!ctx) return CL_EINVAL;
+  if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return CL_ECUDA;
+  if (cudaDeviceSynchronize() != cudaSuccess) return CL_ECUDA;
+  if (enable && !ctx->graph_mode) {
+    const uint64_t init[2] = {ctx->step_index, 0};
+    if (cudaMemcpy(ctx->d_step, init, sizeof(init), cudaMemcpyHostToDevice) != cudaSuccess) return CL_ECUDA;
+  } else if (!enable && ctx->graph_mode) {
+    uint64_t v = 0;
+    if (cudaMemcpy(&v, ctx->d_step, sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess) return CL_ECUDA;
+    ctx->step_index = v;
+  }
+  ctx->graph_mode = enable ? 1 : 0;
   return CL_OK;
 }
 extern "C" int64_t cl_launch_count(const cl_ctx* ctx) { return ctx ? ctx->launches : 0; }

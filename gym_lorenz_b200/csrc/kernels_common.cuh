@@ -19,6 +19,9 @@ struct KParams {
   int64_t n, n_pad, env_id_base;
   uint32_t k0, k1;
   uint64_t step_index;
+  // graph mode: the Philox step index lives on the device so that CUDA-graph replays advance it
+  uint64_t* step_ptr;     // nullptr -> use step_index
+  uint32_t* step_ticket;  // block-completion ticket for the commit
   int32_t max_steps, substeps, flags, reward_f32;
   double dt, alpha, act_limit, act_gain, param_jitter;
   // persistent buffers
@@ -80,10 +83,31 @@ __device__ __forceinline__ Stream make_stream(const KParams& p, int64_t i, uint6
   s.id_lo = (uint32_t)gid;
   s.id_hi = (uint32_t)(gid >> 32);
   s.step = (uint32_t)step;
-  // upper 24 bits of a 56-bit step counter ride in the tag word (see Stream::draw callers)
+  // the upper 24 bits of a 56-bit step counter are folded into the second key word
   s.k0 = p.k0;
   s.k1 = p.k1 ^ (uint32_t)((step >> 32) & 0x00FFFFFFu);
   return s;
+}
+
+// Step index of this launch: by value, or (graph mode) read from the device counter.
+__device__ __forceinline__ uint64_t step_base(const KParams& p) {
+  return p.step_ptr != nullptr ? *((volatile const uint64_t*)p.step_ptr) : p.step_index;
+}
+// Graph mode: the last block to finish advances the device counter.  Every thread read the
+// counter at its start and the block barrier below orders those reads before the block's ticket,
+// so the increment cannot race with a reader.
+__device__ __forceinline__ void step_commit(const KParams& p, uint64_t count) {
+  if (p.step_ptr == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t t = atomicAdd(p.step_ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *p.step_ptr += count;
+      *p.step_ticket = 0u;
+      __threadfence();
+    }
+  }
 }
 
 // n uniforms in [lo,hi) (NumPy construction), 2 per Philox block.
@@ -248,8 +272,9 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
     a_next[c] = (live && p.action != nullptr) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
 
   unsigned bad_acc = 0u;
+  const uint64_t step0 = step_base(p);
   for (int t = 0; t < T; ++t) {
-    const Stream rng = make_stream(p, i, p.step_index + (uint64_t)t);
+    const Stream rng = make_stream(p, i, step0 + (uint64_t)t);
     float a[E::ACT];
     if (ROLL && p.action == nullptr) {
       synth_action<E>(p, rng, a);
@@ -270,6 +295,7 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
     p.ep_len[i] = ep_len;
     p.ep_return[i] = ep_ret;
   }
+  step_commit(p, (uint64_t)T);
 }
 
 // ---- the dynamic rollout kernel ---------------------------------------------------------
@@ -311,11 +337,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
@@ -374,6 +395,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
   // wait below practically never spins (a reserve-ahead scheme doubled the in-flight window and
   // spent 20 % of its samples spinning: profiles/r01_dyn_ncu_source_stalls.txt).
   uint32_t phase = 0u;
+  const uint64_t step0 = step_base(p);
   uint32_t q = grab();
   while (q < total) {
     const uint32_t e = q % W, c = q / W;
@@ -410,7 +432,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     unsigned bad_acc = 0u;
     for (int tl = 0; tl < len; ++tl) {
       const int t = t0 + tl;
-      const Stream rng = make_stream(p, i, p.step_index + (uint64_t)t);
+      const Stream rng = make_stream(p, i, step0 + (uint64_t)t);
       float a[E::ACT];
       if (p.action == nullptr) {
         synth_action<E>(p, rng, a);
@@ -436,23 +458,26 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     if (lane == 0) st_release_u32(p.dyn_progress + e, c + 1u);
     q = grab();
   }
+  step_commit(p, (uint64_t)p.T);
 }
 
 template <class E>
 __global__ void __launch_bounds__(256) k_reset(const KParams p) {
   typedef typename E::real real;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n) return;
-  if (p.mask != nullptr && p.mask[i] == 0) return;
-  typename E::S s = {};
-  E::load(s, p, i);  // keeps persistent fields (Adam-dual state, per-env parameters)
-  const Stream rng = make_stream(p, i, p.step_index);
-  real obs[E::OBS];
-  E::reset(s, p, rng, obs);
-  E::store(s, p, i);
-  p.ep_len[i] = 0;
-  p.ep_return[i] = 0.0;
-  if (p.obs) store_obs<real>(p.obs, 0, p.obs_es, p.obs_cs, i, obs, E::OBS, (p.flags & CL_F_OBS_F64) != 0);
+  const uint64_t step0 = step_base(p);
+  if (i < p.n && (p.mask == nullptr || p.mask[i] != 0)) {
+    typename E::S s = {};
+    E::load(s, p, i);  // keeps persistent fields (Adam-dual state, per-env parameters)
+    const Stream rng = make_stream(p, i, step0);
+    real obs[E::OBS];
+    E::reset(s, p, rng, obs);
+    E::store(s, p, i);
+    p.ep_len[i] = 0;
+    p.ep_return[i] = 0.0;
+    if (p.obs) store_obs<real>(p.obs, 0, p.obs_es, p.obs_cs, i, obs, E::OBS, (p.flags & CL_F_OBS_F64) != 0);
+  }
+  step_commit(p, 1);
 }
 
 template <class E>

@@ -202,9 +202,16 @@ class DeviceRolloutCollector:
     `policy(obs) -> (actions, values, log_probs)` is any torch callable (the learner's network);
     time-limit truncations bootstrap with the value of the terminal observation like SB3
     (`rewards[idx] += gamma * V(terminal_obs)`).
+
+    `use_cuda_graph=True` captures the whole n_steps loop (policy kernels, env step kernels,
+    buffer writes, GAE) into ONE CUDA graph and replays it per rollout: at a few thousand envs the
+    loop is launch-latency bound (~30 small kernels per step), which is exactly what graphs remove.
+    The env is switched to graph mode (device-resident Philox step index), so replays keep
+    advancing the random streams.
     """
 
-    def __init__(self, env, policy: Callable, n_steps: int, gamma: float = 0.99, gae_lambda: float = 0.95):
+    def __init__(self, env, policy: Callable, n_steps: int, gamma: float = 0.99, gae_lambda: float = 0.95,
+                 use_cuda_graph: bool = False):
         self.env, self.policy, self.n_steps = env, policy, int(n_steps)
         self.gamma, self.gae_lambda = gamma, gae_lambda
         b = env.venv.batch if hasattr(env, "venv") else env.batch
@@ -222,11 +229,15 @@ class DeviceRolloutCollector:
         self._last_starts = torch.ones(N, dtype=torch.float32, device=dev)
         self._lo = float(b.layout.act_low)
         self._hi = float(b.layout.act_high)
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graph = None
+        self._graph_out = None
+        self._warm = False
 
-    @torch.no_grad()
-    def collect(self) -> Dict[str, torch.Tensor]:
-        if self._last_obs is None:
-            self._last_obs = self.env.reset_tensor().clone()
+    def _terminal_obs(self):
+        return self.env.terminal_obs() if hasattr(self.env, "terminal_obs") else self.batch.terminal_obs()
+
+    def _loop(self, sync_free: bool) -> Dict[str, torch.Tensor]:
         buf = self.buf
         for t in range(self.n_steps):
             obs = self._last_obs
@@ -239,16 +250,36 @@ class DeviceRolloutCollector:
             new_obs, rew, done = self.env.step_tensor(torch.clamp(actions, self._lo, self._hi))
             rew = rew.float().clone()
             trunc = (done & L.DONE_TRUNCATED).bool() & ~(done & L.DONE_TERMINATED).bool()
-            if bool(trunc.any()):   # TimeLimit bootstrap (SB3 collect_rollouts)
-                term = self.env.terminal_obs() if hasattr(self.env, "terminal_obs") else self.batch.terminal_obs()
-                _, tv, _ = self.policy(term)
+            if sync_free or bool(trunc.any()):   # TimeLimit bootstrap (SB3 collect_rollouts)
+                _, tv, _ = self.policy(self._terminal_obs())
                 rew = torch.where(trunc, rew + self.gamma * tv.view(-1), rew)
             buf["rewards"][t].copy_(rew)
-            self._last_starts = (done != 0).float()
-            self._last_obs = new_obs.clone()
+            self._last_starts.copy_((done != 0).float())
+            self._last_obs.copy_(new_obs)
         _, last_values, _ = self.policy(self._last_obs)
         adv, ret = gae(buf["rewards"], buf["values"], buf["episode_starts"], last_values.view(-1), self._last_starts,
                        self.gamma, self.gae_lambda)
         out = dict(buf)
         out["advantages"], out["returns"] = adv, ret
         return out
+
+    @torch.no_grad()
+    def collect(self) -> Dict[str, torch.Tensor]:
+        if self._last_obs is None:
+            self._last_obs = self.env.reset_tensor().clone()
+        if not self.use_cuda_graph:
+            return self._loop(sync_free=False)
+        if self._graph is None:
+            dev = self.batch.device
+            if not self._warm:
+                # first rollout: eager, sync-free -- it is a real rollout AND the warm-up that
+                # CUDA-graph capture needs (lazy initialisation, allocator, occupancy queries)
+                self.batch.set_graph_mode(True)
+                self._warm = True
+                return self._loop(sync_free=True)
+            torch.cuda.synchronize(dev)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):            # capture executes nothing
+                self._graph_out = self._loop(sync_free=True)
+        self._graph.replay()
+        return self._graph_out

@@ -208,6 +208,13 @@ int cl_stats(cl_ctx* ctx, void* stream, const cl_buffers* buf, double* out8, int
 int cl_get_step_index(const cl_ctx* ctx, uint64_t* out);
 int cl_set_step_index(cl_ctx* ctx, uint64_t value);
 
+/* -- CUDA-graph mode.  When enabled, the Philox step index lives in device memory and is advanced
+ *    by the kernels themselves (last block to finish), so cl_step / cl_rollout / cl_reset can be
+ *    captured into a CUDA graph (e.g. torch.cuda.graph) and REPLAYED: every replay sees a fresh
+ *    step index.  All scratch is allocated at cl_create, nothing allocates during capture.
+ *    cl_get_step_index then synchronises the device. */
+int cl_set_graph_mode(cl_ctx* ctx, int enable);
+
 /* -- HOST-buffer path (the SB3 VecEnv numpy contract: step_async / step_wait;
  *    SB3 DummyVecEnv.step_async/step_wait, call sites code/train.py:100,
  *    code/lorenz_pmsm/train.py:115-118).

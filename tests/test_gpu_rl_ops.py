@@ -169,3 +169,38 @@ def test_device_rollout_collector_matches_sb3_bookkeeping():
         tv = policy(env2.batch.terminal_obs())[1]
     assert torch.allclose(out["rewards"][9], raw_r + 0.99 * tv, rtol=1e-6, atol=1e-6)
     env.close(); env2.close()
+
+
+def test_cuda_graph_collector_equals_eager_collector():
+    """The whole n_steps loop captured in one CUDA graph (env in graph mode: device-resident
+    Philox step index) reproduces the eager loop bit-for-bit, replay after replay -- including
+    auto-resets, whose random initial conditions depend on the advancing step index."""
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n, T = 1024, 12
+    torch.manual_seed(1)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3)).to("cuda:0")
+
+    def policy(obs):                      # deterministic: the two runs must match exactly
+        y = net(obs)
+        return torch.tanh(y[:, :2]), y[:, 2], -(y[:, :2] ** 2).sum(1)
+
+    outs = {}
+    for mode in (False, True):
+        env = BatchedChaosVecEnv("hr_sync", n, seed=9, max_episode_steps=5)
+        col = rl_ops.DeviceRolloutCollector(env, policy, n_steps=T, use_cuda_graph=mode)
+        rolls = []
+        for _ in range(3):
+            o = col.collect()
+            torch.cuda.synchronize()
+            rolls.append({k: v.clone() for k, v in o.items()})
+        outs[mode] = (rolls, env.batch.step_index, env.stats())
+        env.close()
+    for r_e, r_g in zip(outs[False][0], outs[True][0]):
+        for k in r_e:
+            assert torch.equal(r_e[k], r_g[k]), k
+    assert outs[False][1] == outs[True][1]             # same number of Philox steps consumed
+    assert outs[False][2]["episodes"] == outs[True][2]["episodes"] > 0
+    # and the rollouts differ from one another (the streams really advance across replays)
+    assert not torch.equal(outs[True][0][0]["obs"], outs[True][0][1]["obs"])

@@ -57,18 +57,18 @@ def numpy_path():
     return N * T / el
 
 
-def tensor_path():
+def tensor_path(graph=False):
     env = BatchedChaosVecEnv("hr_sync", N, seed=0)
     pol = ActorCritic().to("cuda:0")
-    col = rl_ops.DeviceRolloutCollector(env, pol, n_steps=T, gamma=0.99, gae_lambda=0.95)
-    col.collect(); torch.cuda.synchronize()
+    col = rl_ops.DeviceRolloutCollector(env, pol, n_steps=T, gamma=0.99, gae_lambda=0.95, use_cuda_graph=graph)
+    col.collect(); col.collect(); torch.cuda.synchronize()
     t0 = time.perf_counter(); out = col.collect(); torch.cuda.synchronize(); el = time.perf_counter() - t0
     env.close()
     return N * T / el
 
 
 if __name__ == "__main__":
-    a, b = numpy_path(), tensor_path()
+    a, b, c = numpy_path(), tensor_path(False), tensor_path(True)
     print(json.dumps({"config": f"cfg5: HR env x {N}, {T}-step rollout, MlpPolicy-shaped actor-critic",
-                      "numpy_path_cpu_policy_fps": a, "tensor_path_gpu_policy_fps": b,
+                      "numpy_path_cpu_policy_fps": a, "tensor_path_gpu_policy_fps": b, "tensor_path_cuda_graph_fps": c,
                       "reference_ppo_fps_1env_windows_desktop": 1757}))
