@@ -106,6 +106,7 @@ SYMBOLS = [
     ("cl_set_step_index", C.c_int, [_VP, C.c_uint64]),
     ("cl_set_graph_mode", C.c_int, [_VP, C.c_int]),
     ("cl_host_action_staging", C.c_int, [_VP, C.POINTER(_VP)]),
+    ("cl_host_set_zero_copy", C.c_int, [_VP, C.c_int]),
     ("cl_step_host_async", C.c_int, [_VP, _VP, C.POINTER(Buffers), _VP]),
     ("cl_step_host_wait", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_int64)]),
     ("cl_step_host_wait_view", C.c_int, [_VP, _VP, C.POINTER(HostView)]),

@@ -60,6 +60,7 @@ struct HostStage {
   int cur;        // slot being filled / last filled
   cudaStream_t stream;
   bool pending;
+  bool zero_copy;
 };
 
 }  // namespace
@@ -455,6 +456,9 @@ static int host_stage_init(cl_ctx* ctx) {
   }
   h.cur = 0;
   h.pending = false;
+  // default: zero-copy (measured 135 vs 146 us per step at 65,536 envs, 30 vs 37 us at 4,096);
+  // CHAOS_B200_ZEROCOPY=0 selects the DMA-copy chain
+  h.zero_copy = !(getenv("CHAOS_B200_ZEROCOPY") != nullptr && getenv("CHAOS_B200_ZEROCOPY")[0] == '0');
   h.ready = true;
   return CL_OK;
 }
@@ -483,12 +487,18 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
   cudaStream_t st = host_stream(ctx, stream);
   if (action_host && action_host != h.h_act) memcpy(h.h_act, action_host, N * A * sizeof(float));
   CU(cudaSetDevice(ctx->cfg.device));
-  CU(cudaMemcpyAsync(h.d_act, h.h_act, N * A * sizeof(float), cudaMemcpyHostToDevice, st));
+  // Zero-copy mode: the step kernel reads the actions from, and writes obs / reward / done to,
+  // the pinned host buffers directly (UVA-mapped), so both PCIe directions are driven by the SMs
+  // concurrently instead of a serial H2D -> kernel -> D2H chain of DMA copies.
+  const bool zc = h.zero_copy;
+  h.cur = (h.cur + 1) % kHostRing;
+  HostSlot& s = h.slot[h.cur];
+  if (!zc) CU(cudaMemcpyAsync(h.d_act, h.h_act, N * A * sizeof(float), cudaMemcpyHostToDevice, st));
   cl_io io;
   memset(&io, 0, sizeof(io));
-  io.action = h.d_act; io.act_es = (int64_t)A; io.act_cs = 1;
-  io.obs = h.d_obs; io.obs_es = (int64_t)O; io.obs_cs = 1;
-  io.reward = h.d_rew; io.done = h.d_done; io.term_obs = h.d_term;
+  io.action = zc ? h.h_act : h.d_act; io.act_es = (int64_t)A; io.act_cs = 1;
+  io.obs = zc ? s.obs : h.d_obs; io.obs_es = (int64_t)O; io.obs_cs = 1;
+  io.reward = zc ? s.reward : h.d_rew; io.done = zc ? s.done : h.d_done; io.term_obs = h.d_term;
   io.last_ep_ret = h.d_ler; io.last_ep_len = h.d_lel;
   KParams p;
   r = fill_params(ctx, buf, &io, p);
@@ -498,14 +508,18 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
   r = launch(ctx, p, cl::MODE_STEP, st);
   if (r) return r;
   ctx->step_index += 1;
-  h.cur = (h.cur + 1) % kHostRing;
-  HostSlot& s = h.slot[h.cur];
-  CU(cudaMemcpyAsync(s.out, h.d_out, h.out_bytes, cudaMemcpyDeviceToHost, st));
+  if (!zc) CU(cudaMemcpyAsync(s.out, h.d_out, h.out_bytes, cudaMemcpyDeviceToHost, st));
   h.pending = true;
   return CL_OK;
 }
 
-
+extern "C" int cl_host_set_zero_copy(cl_ctx* ctx, int enable) {
+  if (!ctx) return CL_EINVAL;
+  int r = host_stage_init(ctx);
+  if (r) return r;
+  ctx->hs.zero_copy = enable != 0;
+  return CL_OK;
+}
 
 static int host_wait_common(cl_ctx* ctx, void* stream, int64_t* n_done_out) {
   HostStage& h = ctx->hs;

@@ -157,6 +157,27 @@ __device__ __forceinline__ void store_obs(void* base, int64_t off, int64_t es, i
   }
 }
 
+// Row-major [N][OBS] float32 observations (what a policy network and the SB3 host path want):
+// a warp's 32 rows are one contiguous run of 32*OBS floats.  Writing them lane-by-lane would be
+// OBS strided 4-byte stores per lane; instead the warp transposes through shared memory and
+// writes whole 16-byte vectors, i.e. full 128-byte lines (this is what makes direct stores to
+// pinned host memory over PCIe efficient in the zero-copy host path).
+template <typename real, int OBS>
+__device__ __forceinline__ void store_obs_rows_warp(float* __restrict__ sm, float* __restrict__ base,
+                                                    const int64_t warp_env0, const int64_t n, const unsigned lane,
+                                                    const real* obs) {
+#pragma unroll
+  for (int c = 0; c < OBS; ++c) sm[lane * OBS + c] = (float)obs[c];
+  __syncwarp();
+  const int64_t rows = n - warp_env0;
+  const int nflt = (int)(rows >= 32 ? 32 : (rows > 0 ? rows : 0)) * OBS;
+  float* dst = base + warp_env0 * OBS;
+  for (int k = (int)lane * 4; k + 3 < nflt; k += 128)
+    *reinterpret_cast<float4*>(dst + k) = *reinterpret_cast<const float4*>(sm + k);
+  for (int k = (nflt & ~3) + (int)lane; k < nflt; k += 32) dst[k] = sm[k];
+  __syncwarp();
+}
+
 // ---- one control interval of one env (shared by the static and the dynamic kernels) ----
 
 template <class E, bool ROLL>
@@ -164,7 +185,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
                                              const KParams& p, const int64_t i, const bool live,
                                              const unsigned lane, const int t, const Stream& rng,
                                              const float* a, const bool want_noise, const bool obs64,
-                                             const bool autoreset, unsigned& bad_acc) {
+                                             const bool autoreset, unsigned& bad_acc, float* sm_rows) {
   typedef typename E::real real;
   double nz[E::NOISE > 0 ? E::NOISE : 1];
   nz[0] = 0.0;
@@ -209,19 +230,23 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
   bad_acc += __popc(bm);  // flushed once per launch / task (diverged envs would otherwise
                           // serialise every warp on one atomic each interval)
 
-  if (live) {
-    const int64_t oo = ROLL ? t * p.obs_ts : 0;
-    if (done) {
-      if (p.term_obs) store_obs<real>(p.term_obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
-      if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;
-      if (p.last_ep_len) p.last_ep_len[i] = ep_len;
-      if (autoreset) {
-        E::reset(s, p, rng, obs);
-        ep_len = 0;
-        ep_ret = 0.0;
-      }
+  const int64_t oo = ROLL ? t * p.obs_ts : 0;
+  if (live && done) {
+    if (p.term_obs) store_obs<real>(p.term_obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
+    if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;
+    if (p.last_ep_len) p.last_ep_len[i] = ep_len;
+    if (autoreset) {
+      E::reset(s, p, rng, obs);
+      ep_len = 0;
+      ep_ret = 0.0;
     }
-    if (p.obs) store_obs<real>(p.obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
+  }
+  // warp-uniform: contiguous float32 rows -> coalesced vector stores through shared memory
+  const bool rows_fast = p.obs != nullptr && !obs64 && p.obs_cs == 1 && p.obs_es == E::OBS;
+  if (rows_fast)
+    store_obs_rows_warp<real, E::OBS>(sm_rows, (float*)p.obs + oo, i - (int64_t)lane, p.n, lane, obs);
+  if (live) {
+    if (p.obs && !rows_fast) store_obs<real>(p.obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
     if (p.reward) {
       const int64_t ro = (ROLL ? t * p.rew_ts : 0) + i;
       if (p.reward_f32) ((float*)p.reward)[ro] = (float)rew;
@@ -246,9 +271,11 @@ __device__ __forceinline__ void synth_action(const KParams& p, const Stream& rng
 
 template <class E, bool ROLL>
 __global__ void __launch_bounds__(256) k_step(const KParams p) {
+  __shared__ __align__(16) float sm_rows_all[8][32 * E::OBS];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < p.n;
   const unsigned lane = threadIdx.x & 31u;
+  float* sm_rows = sm_rows_all[threadIdx.x >> 5];
 
   typename E::S s = {};
   int32_t ep_len = 0;
@@ -287,7 +314,7 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
           a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
       }
     }
-    env_interval<E, ROLL>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc);
+    env_interval<E, ROLL>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc, sm_rows);
   }
   if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
   if (live) {
@@ -350,8 +377,10 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
 template <class E>
 __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ __align__(16) float sm_rows_all[4][32 * E::OBS];
   const unsigned lane = threadIdx.x & 31u;
   const int wib = threadIdx.x >> 5;
+  float* sm_rows = sm_rows_all[wib];
   const int wpb = blockDim.x >> 5;
   const int Tc = p.dyn_chunk;
   const int per_buf = Tc * E::ACT * 32;  // floats
@@ -444,7 +473,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
         for (int cc = 0; cc < E::ACT; ++cc)
           a[cc] = live ? p.action[(int64_t)t * p.act_ts + i * p.act_es + cc * p.act_cs] : 0.0f;
       }
-      env_interval<E, true>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc);
+      env_interval<E, true>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc, sm_rows);
     }
     if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
     bad_acc = 0u;

@@ -238,6 +238,9 @@ typedef struct cl_host_view {
   int64_t n_done;
 } cl_host_view;
 int cl_host_action_staging(cl_ctx* ctx, float** action_pinned);
+/* zero-copy variant of the host path: the step kernel reads actions from / writes results to the
+ * pinned (UVA-mapped) host buffers directly instead of DMA copies around it */
+int cl_host_set_zero_copy(cl_ctx* ctx, int enable);
 int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* buf, const float* action_host);
 int cl_step_host_wait(cl_ctx* ctx, void* stream, float* obs_host, float* reward_host,
                       uint8_t* done_host, float* term_obs_host, double* last_ep_ret_host,
