@@ -281,7 +281,7 @@ def run_b200(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-        fp64_peak = measure_fma_peak(local, fma_bytes, 0.5)
+        fp64_peak = measure_fma_peak(local, fma_bytes, 0.2)
         flops = float(N) * T * S * flop_sub
         ach = flops / (kern_ms * 1e-3) * 1e-12
         gbs = float(N) * T * bytes_step / (kern_ms * 1e-3) * 1e-9

@@ -359,7 +359,7 @@ struct EnvPMSMSync {
 #pragma unroll
     for (int c = 0; c < 3; ++c) { s.a[c] = ldp<float>(p, c, i); s.b[c] = ldp<float>(p, 3 + c, i); }
     s.lam = ldp<float>(p, 6, i); s.m = ldp<float>(p, 7, i); s.v = ldp<float>(p, 8, i);
-    s.adam = p.aux_int[i];
+    s.adam = __ldcg(p.aux_int + i);  // L1-bypassing like every per-env load (see k_rollout_dyn)
   }
   __device__ static void store(const S& s, const KParams& p, int64_t i) {
 #pragma unroll

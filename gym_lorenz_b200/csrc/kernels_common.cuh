@@ -438,9 +438,11 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
       stage(q, 0);
     }
     if (c > 0) {
+      // No acquire fence on the reader: every plane / counter load below bypasses L1 (ld.cg), so
+      // it is served by L2, the point of coherence, where the writer's release made the data
+      // visible before the flag.  (An acquire would add an L1 invalidate + error barrier per task.)
       if (lane == 0) {
         while (ld_relaxed_u32(p.dyn_progress + e) < c) __nanosleep(32);
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
       }
       __syncwarp();
     }

@@ -178,3 +178,26 @@ def test_dynamic_rollout_is_selected_automatically_at_65536(monkeypatch):
     b2.rollout(16, want=("reward",))
     assert b2.dyn_launch_count == 0         # 32768 env-warps: 98.8 % static balance
     b.close(); b2.close()
+
+
+@pytest.mark.parametrize("kind", ["pmsm_sync", "hr_sync", "lorenz_rk4"])
+def test_dynamic_rollout_many_handoffs_stress(kind, monkeypatch):
+    """26 chunks per env-warp, repeated: every chunk boundary hands an env-warp's planes (and,
+    for PMSM, its int32 Adam counter) from one SM to another through L2."""
+    import torch
+    n, T = 70000, 203
+    ref = None
+    for rep, mode in enumerate(("0", "1", "1", "1")):
+        monkeypatch.setenv("CHAOS_B200_DYN", mode)
+        b = H.gpu_batch(kind, n, seed=21, autoreset=True, max_episode_steps=50)
+        b.reset()
+        out = b.rollout(T, None, want=("reward", "done"))      # in-kernel Philox actions
+        torch.cuda.synchronize()
+        cur = (out["reward"][:, :n].clone(), out["done"][:, :n].clone(), b.state.clone(), b.aux_int.clone(),
+               b.ep_len.clone(), b.ep_return.clone())
+        if ref is None:
+            ref = cur
+        else:
+            for x, y in zip(ref, cur):
+                assert torch.equal(torch.nan_to_num(x.double()), torch.nan_to_num(y.double())), (kind, rep)
+        b.close()

@@ -57,6 +57,28 @@ __global__ void __launch_bounds__(1024) k_half(int iters, int active, const doub
   if (s == -1.2345) out[0] = s;
 }
 
+// conversion throughput (11 F2F per control interval in the env kernel)
+template <int MODE>
+__global__ void __launch_bounds__(1024) k_cvt(int iters, const float* in, double* out) {
+  float f[8]; double d[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { f[j] = in[threadIdx.x + j]; d[j] = (double)f[j] * 1.000001; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (MODE == 0) { d[j] = (double)f[j]; f[j] = __int_as_float(__float_as_int(f[j]) ^ (int)__double2loint(d[j])); }   // F2F.F64.F32 (+ cheap int ops)
+        if (MODE == 1) { f[j] = (float)d[j]; d[j] = __hiloint2double(__double2hiint(d[j]), __float_as_int(f[j])); }     // F2F.F32.F64
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += d[j] + (double)f[j];
+  if (s == -1.2345) out[0] = s;
+}
+
 // ---------------- RK4 variants ------------------------------------------------------------
 struct Par { double sigma, rho, beta; };
 __device__ __forceinline__ void rhs(const Par& q, double x, double y, double z, double u1, double u2, double u3,
@@ -135,6 +157,25 @@ __global__ void __launch_bounds__(256) k_rk4_il2(const Args a, int T, int n, con
   out[i0] = x0 + x1; out[n + i0] = y0 + y1; out[2 * n + i0] = z0 + z1;
 }
 
+// persistent-style balanced launch: exactly `wps` warps per scheduler, each thread integrates
+// `reps` envs one after another (compute only) -- what the RK4 loop can reach at 3 vs 4 warps
+template <int VAR>
+__global__ void __launch_bounds__(128) k_rk4_bal(const Args a, int T, int reps, int n, const double* st, double* out) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  Par q; q.sigma = a.sigma; q.rho = a.rho; q.beta = a.beta;
+  double acc = 0;
+  for (int r = 0; r < reps; ++r) {
+    const int i = (tid + r * 7919) % n;
+    double x = st[i], y = st[n + i], z = st[2 * n + i];
+    for (int t = 0; t < T; ++t) {
+      const double u1 = 1e-3 * (double)(t & 7), u2 = -u1, u3 = 0.5 * u1;
+      rk4(q, x, y, z, u1, u2, u3, a.h, a.hh, a.h3, a.h6, a.S);
+    }
+    acc += x + y + z;
+  }
+  out[tid % n] = acc;
+}
+
 template <typename F>
 float time_ms(F launch, int reps) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -190,6 +231,29 @@ int main() {
     auto L = [&]() { k_half<<<sms, 512>>>(iters, active, in, out); };
     float ms = time_ms(L, 5);
     printf("active lanes=%2d  %8.3f ms  %.2f cyc/warp-instr\n", active, ms, ms * 1e-3 * 1.965e9 / ((double)iters * 64.0 * 4));
+  }
+  printf("\n== 1c. F2F conversion cost (4 warps/SMSP; each iteration = 32 conversions + 32 int ops per thread) ==\n");
+  {
+    float* fin; CK(cudaMalloc(&fin, 4096 * 4)); CK(cudaMemset(fin, 0x3c, 4096 * 4));
+    for (int m = 0; m < 2; ++m) {
+      auto L = [&]() { if (m == 0) k_cvt<0><<<sms, 512>>>(2000, fin, out); else k_cvt<1><<<sms, 512>>>(2000, fin, out); };
+      float ms = time_ms(L, 5);
+      printf("%s  %8.3f ms  %.2f cyc per warp-conversion per SMSP (upper bound, includes the int op)\n",
+             m == 0 ? "F2F.F64.F32" : "F2F.F32.F64", ms, ms * 1e-3 * 1.965e9 / (2000.0 * 32.0 * 4));
+    }
+  }
+  printf("\n== 1d. pure RK4 loop (uniform params, const operands), balanced persistent launch: warps/SMSP vs TFLOP/s(87) ==\n");
+  {
+    Args a; a.dt = 0.01; a.S = 16; a.h = a.dt / 16; a.hh = 0.5 * a.h; a.h3 = a.h / 3; a.h6 = a.h / 6;
+    a.sigma = 10; a.rho = 28; a.beta = 8.0 / 3.0;
+    for (int wps = 1; wps <= 6; ++wps) {
+      const int grid = sms * wps, T = 16, reps = 4;
+      auto L = [&]() { k_rk4_bal<2><<<grid, 128>>>(a, T, reps, 65536, in, out); };
+      float ms = time_ms(L, 5);
+      const double sub = (double)grid * 128 * reps * T * a.S;
+      printf("warps/SMSP=%d  %8.3f ms  %.2f TFLOP/s(87)  = %.1f%% of 36.6\n", wps, ms, sub * 87 / (ms * 1e-3) * 1e-12,
+             sub * 87 / (ms * 1e-3) * 1e-12 / 36.6 * 100);
+    }
   }
   if (getenv("PROBE_SHORT")) return 0;
   printf("\n== 2. Lorenz RK4 loop variants, N=65536, S=16, T=64 (4096 substeps/env... x) ==\n");
