@@ -230,7 +230,7 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
   p.n = c.num_envs; p.n_pad = c.n_pad; p.env_id_base = c.env_id_base;
   p.k0 = (uint32_t)c.seed; p.k1 = (uint32_t)(c.seed >> 32);
   p.step_index = ctx->step_index;
-  if (ctx->graph_mode) { p.step_ptr = ctx->d_step; p.step_ticket = (uint32_t*)(ctx->d_step + 1); }
+  if (ctx->graph_mode) p.step_ptr = ctx->d_step;
   p.max_steps = c.max_episode_steps; p.substeps = c.substeps; p.flags = c.flags;
   p.dt = c.dt; p.alpha = c.alpha; p.act_limit = c.act_limit; p.act_gain = c.act_gain;
   p.param_jitter = c.param_jitter;
@@ -256,11 +256,19 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
   return CL_OK;
 }
 
+__global__ void k_advance_step(uint64_t* step, uint64_t count) { *step += count; }
+
 static int launch(cl_ctx* ctx, const KParams& p, int mode, cudaStream_t st) {
   cudaError_t e = is_parity(ctx->cfg.kind) ? cl_launch_parity(ctx->cfg.kind, p, mode, st, ctx->block)
                                            : cl_launch_northstar(ctx->cfg.kind, p, mode, st, ctx->block);
   if (e != cudaSuccess) return fail(ctx, CL_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   ctx->launches += 1;
+  if (ctx->graph_mode && mode != cl::MODE_INIT) {  // device-resident Philox step index (CUDA graphs)
+    const uint64_t count = (mode == cl::MODE_ROLLOUT || mode == cl::MODE_ROLLOUT_DYN) ? (uint64_t)p.T : 1;
+    k_advance_step<<<1, 1, 0, st>>>(ctx->d_step, count);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, CL_ECUDA, "step-index advance failed: %s", cudaGetErrorString(e));
+  }
   return CL_OK;
 }
 

@@ -21,7 +21,6 @@ struct KParams {
   uint64_t step_index;
   // graph mode: the Philox step index lives on the device so that CUDA-graph replays advance it
   uint64_t* step_ptr;     // nullptr -> use step_index
-  uint32_t* step_ticket;  // block-completion ticket for the commit
   int32_t max_steps, substeps, flags, reward_f32;
   double dt, alpha, act_limit, act_gain, param_jitter;
   // persistent buffers
@@ -93,22 +92,10 @@ __device__ __forceinline__ Stream make_stream(const KParams& p, int64_t i, uint6
 __device__ __forceinline__ uint64_t step_base(const KParams& p) {
   return p.step_ptr != nullptr ? *((volatile const uint64_t*)p.step_ptr) : p.step_index;
 }
-// Graph mode: the last block to finish advances the device counter.  Every thread read the
-// counter at its start and the block barrier below orders those reads before the block's ticket,
-// so the increment cannot race with a reader.
-__device__ __forceinline__ void step_commit(const KParams& p, uint64_t count) {
-  if (p.step_ptr == nullptr) return;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const uint32_t t = atomicAdd(p.step_ticket, 1u);
-    if (t == gridDim.x - 1) {
-      *p.step_ptr += count;
-      *p.step_ticket = 0u;
-      __threadfence();
-    }
-  }
-}
+// Graph mode: a one-thread kernel enqueued right after each env kernel advances the device
+// counter (a per-block completion ticket would put one same-address atomic per block on the
+// critical path: +35 us at 16,384 blocks).
+__global__ void k_advance_step(uint64_t* step, uint64_t count);
 
 // n uniforms in [lo,hi) (NumPy construction), 2 per Philox block.
 template <int N>
@@ -271,11 +258,11 @@ __device__ __forceinline__ void synth_action(const KParams& p, const Stream& rng
 
 template <class E, bool ROLL>
 __global__ void __launch_bounds__(256) k_step(const KParams p) {
-  __shared__ __align__(16) float sm_rows_all[8][32 * E::OBS];
+  extern __shared__ __align__(16) float sm_rows_all[];  // [warps per block][32 * OBS], row-store staging
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < p.n;
   const unsigned lane = threadIdx.x & 31u;
-  float* sm_rows = sm_rows_all[threadIdx.x >> 5];
+  float* sm_rows = sm_rows_all + (threadIdx.x >> 5) * (32 * E::OBS);
 
   typename E::S s = {};
   int32_t ep_len = 0;
@@ -322,7 +309,6 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
     p.ep_len[i] = ep_len;
     p.ep_return[i] = ep_ret;
   }
-  step_commit(p, (uint64_t)T);
 }
 
 // ---- the dynamic rollout kernel ---------------------------------------------------------
@@ -438,11 +424,12 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
       stage(q, 0);
     }
     if (c > 0) {
-      // No acquire fence on the reader: every plane / counter load below bypasses L1 (ld.cg), so
-      // it is served by L2, the point of coherence, where the writer's release made the data
-      // visible before the flag.  (An acquire would add an L1 invalidate + error barrier per task.)
+      // relaxed polling, then one acquire fence: pairs with the writer's release store.  (All
+      // per-env loads below additionally bypass L1; dropping the fence measured only +0.7 %, so
+      // the formally synchronised version is kept.)
       if (lane == 0) {
         while (ld_relaxed_u32(p.dyn_progress + e) < c) __nanosleep(32);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
       }
       __syncwarp();
     }
@@ -489,7 +476,6 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     if (lane == 0) st_release_u32(p.dyn_progress + e, c + 1u);
     q = grab();
   }
-  step_commit(p, (uint64_t)p.T);
 }
 
 template <class E>
@@ -508,7 +494,6 @@ __global__ void __launch_bounds__(256) k_reset(const KParams p) {
     p.ep_return[i] = 0.0;
     if (p.obs) store_obs<real>(p.obs, 0, p.obs_es, p.obs_cs, i, obs, E::OBS, (p.flags & CL_F_OBS_F64) != 0);
   }
-  step_commit(p, 1);
 }
 
 template <class E>
@@ -524,11 +509,18 @@ __global__ void __launch_bounds__(256) k_init(const KParams p) {
 }
 
 template <class E>
+inline size_t row_smem(const KParams& p, int block) {
+  const bool rows = p.obs != nullptr && !(p.flags & CL_F_OBS_F64) && p.obs_cs == 1 && p.obs_es == E::OBS;
+  return rows ? (size_t)(block / 32) * 32 * E::OBS * sizeof(float) : 0;
+}
+
+template <class E>
 cudaError_t launch_env(const KParams& p, int mode, cudaStream_t st, int block) {
   const unsigned grid = (unsigned)((p.n + block - 1) / block);
   switch (mode) {
-    case MODE_STEP: k_step<E, false><<<grid, block, 0, st>>>(p); break;
-    case MODE_ROLLOUT: k_step<E, true><<<grid, block, 0, st>>>(p); break;
+    // dynamic smem only when observations go out as contiguous float32 rows (row-store staging)
+    case MODE_STEP: k_step<E, false><<<grid, block, row_smem<E>(p, block), st>>>(p); break;
+    case MODE_ROLLOUT: k_step<E, true><<<grid, block, row_smem<E>(p, block), st>>>(p); break;
     case MODE_RESET: k_reset<E><<<grid, block, 0, st>>>(p); break;
     case MODE_INIT: k_init<E><<<grid, block, 0, st>>>(p); break;
     case MODE_ROLLOUT_DYN: {

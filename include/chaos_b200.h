@@ -209,7 +209,7 @@ int cl_get_step_index(const cl_ctx* ctx, uint64_t* out);
 int cl_set_step_index(cl_ctx* ctx, uint64_t value);
 
 /* -- CUDA-graph mode.  When enabled, the Philox step index lives in device memory and is advanced
- *    by the kernels themselves (last block to finish), so cl_step / cl_rollout / cl_reset can be
+ *    by a one-thread kernel enqueued right after each env kernel, so cl_step / cl_rollout / cl_reset can be
  *    captured into a CUDA graph (e.g. torch.cuda.graph) and REPLAYED: every replay sees a fresh
  *    step index.  All scratch is allocated at cl_create, nothing allocates during capture.
  *    cl_get_step_index then synchronises the device. */

@@ -31,6 +31,8 @@ KINDS = {
     "lorenz_rk4": ({"substeps": 16}, 1.0, 48 + 12 + 48 + 24 + 8 + 1 + 12, 16 * 87),
     "lorenz_rk4_f32": ({"substeps": 16}, 1.0, 24 + 12 + 24 + 24 + 4 + 1 + 12, 16 * 87),
     "pmsm_rk4": ({"substeps": 4}, 1.0, 64 + 8 + 64 + 24 + 8 + 1 + 12, 4 * 2 * 91),
+    "memristive4_pair": ({}, 2.0, 72 + 12 + 72 + 32 + 8 + 1 + 12, 95),
+    "pmsm_free": ({}, 0.0, 32 + 8 + 32 + 24 + 8 + 1 + 12, 34),
 }
 
 
@@ -70,7 +72,18 @@ def main():
             soa = (torch.rand((T, b.act_dim, b.n_pad), generator=g, device=dev) * 2 - 1) * amp
             acts = soa[:, :, :n].permute(0, 2, 1)
             a0 = acts[0]
-            ms_step = timed(lambda: b.step(a0), 200 if n <= 65536 else 50)
+            # single steps are timed as a CUDA-graph replay of 20 launches (graph mode keeps the Philox
+            # step index on the device), so the number is kernel time, not Python/ctypes call overhead
+            b.set_graph_mode(True)
+            for _ in range(3):
+                b.step(a0)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(20):
+                    b.step(a0)
+            ms_step = timed(g.replay, 20 if n <= 65536 else 5) / 20
+            ms_step_eager = timed(lambda: b.step(a0), 100 if n <= 65536 else 30)
             out = b.rollout(T, acts)
             ms_roll = timed(lambda: b.rollout(T, acts, out=out), 20 if n <= 65536 else 5)
             peak_tf = fp32 if b.real == torch.float32 and kind != "pmsm_sync" else fp64
@@ -81,7 +94,8 @@ def main():
                     "kind": kind, "n": n, "mode": mode, "T": steps, "ms_per_launch": round(ms, 5),
                     "env_steps_per_s": rate, "gbs": rate * byts * 1e-9, "hbm_frac": rate * byts * 1e-9 / hbm,
                     "tflops": rate * flop * 1e-12, "fma_frac": rate * flop * 1e-12 / peak_tf,
-                    "dyn": b.dyn_launch_count > 0, "block": b.block_size}), flush=True)
+                    "dyn": b.dyn_launch_count > 0, "block": b.block_size,
+                    "eager_python_ms_per_step": round(ms_step_eager, 5) if mode == "step" else None}), flush=True)
             b.close()
             del b, soa, acts, out
             torch.cuda.empty_cache()
