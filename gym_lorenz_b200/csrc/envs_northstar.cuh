@@ -247,7 +247,7 @@ struct EnvPMSMRK4 {
     observe(s, obs);
     const double e0 = fabs(obs[0]), e1 = fabs(obs[1]), e2 = fabs(obs[2]);
     const double E = e0 + e1 + e2;
-    rew = -E - (pow(e0 + 1e-6, p.alpha) + pow(e1 + 1e-6, p.alpha) + pow(e2 + 1e-6, p.alpha));
+    rew = -E - (pow_pos(e0 + 1e-6, p.alpha) + pow_pos(e1 + 1e-6, p.alpha) + pow_pos(e2 + 1e-6, p.alpha));
     term = false;
     if (!(E <= 1000.0)) { rew = -1000.0; term = true; }  // lorenz_env_try_pmsm.py:174-176
   }

@@ -449,7 +449,7 @@ struct EnvPMSMSync {
     const float al = (float)p.alpha;
     float fp[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) fp[c] = (float)pow((double)__fadd_rn(e[c], (float)1e-6), (double)al);
+    for (int c = 0; c < 3; ++c) fp[c] = (float)pow_pos((double)__fadd_rn(e[c], (float)1e-6), (double)al);
     const float frac = __fadd_rn(__fadd_rn(fp[0], fp[1]), fp[2]);
     // :165 uses the RAW action
     const float apen = __fmul_rn(s.lam, __fadd_rn(__fmul_rn(act[0], act[0]), __fmul_rn(act[1], act[1])));
@@ -520,7 +520,7 @@ struct EnvPMSMClassic {
     }
     observe(s, obs);
     const double E = ((0.0 + fabs(obs[0])) + fabs(obs[1])) + fabs(obs[2]);
-    rew = (-E) - pow(E, 1.0 / 10);  // :122
+    rew = (-E) - pow_pos(E, 1.0 / 10);  // :122
     s.t = s.t + 0.01;
     term = (s.t == 5.0) || (rew < -1e6);
   }
@@ -639,7 +639,7 @@ struct EnvMemristive4Pair {
     for (int c = 0; c < 4; ++c) s.b[c] = s.b[c] + (d[c] * 0.001);
     observe(s, obs);
     const double E = (((0.0 + fabs(obs[0])) + fabs(obs[1])) + fabs(obs[2])) + fabs(obs[3]);
-    rew = (-E) - pow(E, 1.0 / 3);
+    rew = (-E) - pow_pos(E, 1.0 / 3);
     s.t = s.t + 0.001;
     term = (s.t == 5.0) || (rew < -1e6);
   }

@@ -76,6 +76,16 @@ __device__ __forceinline__ double clipd(double a, double lo, double hi) {
   return a < lo ? lo : (a > hi ? hi : a);
 }
 
+// x**a for x >= 0 (reward terms): exp(a*log(x)) costs roughly half of the fully general double
+// pow() and is accurate to ~1e-15 relative here (|a*log x| stays below ~10), far inside the
+// tolerances of the quantities it feeds (1 ulp f32 after rounding / 1e-12 in f64).  The general
+// pow() handles the exceptional exponents.
+__device__ __forceinline__ double pow_pos(double x, double a) {
+  if (!(a > 0.0) || !(a < 64.0)) return pow(x, a);
+  if (x == 0.0) return 0.0;
+  return exp(a * log(x));   // log(inf)=inf -> inf, NaN propagates, x<0 -> NaN like pow for non-integer a
+}
+
 __device__ __forceinline__ Stream make_stream(const KParams& p, int64_t i, uint64_t step) {
   const uint64_t gid = (uint64_t)(p.env_id_base + i);
   Stream s;
@@ -188,12 +198,14 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
   real obs[E::OBS];
   real rew;
   bool term;
+  const bool was_finite = E::finite(s);
   E::step(s, p, a, nz, obs, rew, term);
   ep_len += 1;
   ep_ret += (double)rew;
   const bool trunc = E::time_limit(p, ep_len);
   const bool done = term || trunc;
-  const bool bad = !E::finite(s);
+  const bool bad = was_finite && !E::finite(s);  // divergence EVENT (a diverged env that is never
+                                                 // reset would otherwise cost an atomic every step)
 
   // warp-aggregated statistics (one set of atomics per warp, only when something ended)
   const unsigned dm = __ballot_sync(0xffffffffu, live && done && autoreset);

@@ -71,7 +71,7 @@ typedef enum cl_env_kind {
 #define CL_STAT_RET_SUM 1    /* sum of episode returns                  */
 #define CL_STAT_RET_SQ 2     /* sum of squared episode returns          */
 #define CL_STAT_LEN_SUM 3    /* sum of episode lengths                  */
-#define CL_STAT_NONFINITE 4  /* env-steps that ended in a non-finite state */
+#define CL_STAT_NONFINITE 4  /* divergence events: env-steps that turned a finite state non-finite */
 #define CL_STAT_TERMINATED 5 /* episodes ended by the env's own guard   */
 #define CL_STAT_TRUNCATED 6  /* episodes ended by the TimeLimit         */
 #define CL_STAT_RESERVED 7

@@ -620,11 +620,12 @@ void orc_rollout(const orc_cfg* cfg, int T, double synth_amp, void* state, int32
         }
         double o[8], rew;
         int term;
+        const int was_finite = env_finite(kind, &e);
         env_step(cfg, &e, a, nz, o, &rew, &term);
         len += 1; ret += rew;
         int trunc = time_limit(cfg, len);
         int dn = term || trunc;
-        if (!env_finite(kind, &e)) ls[4] += 1;
+        if (was_finite && !env_finite(kind, &e)) ls[4] += 1;  /* divergence event */
         if (dn) {
           if (term_obs) for (int c = 0; c < no; ++c) term_obs[((int64_t)t * no + c) * np_ + i] = o[c];
           if (last_ep_ret) last_ep_ret[i] = ret;

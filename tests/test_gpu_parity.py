@@ -135,7 +135,7 @@ def test_gpu_vs_oracle_seeded_batch_with_autoreset(oracle_api, kind, kw, amp):
             assert np.array_equal(b.last_ep_len.cpu().numpy()[:n][m], extra["last_ep_len"][:n][m])
             H.assert_close(b.last_ep_ret.cpu().numpy()[:n][m], extra["last_ep_ret"][:n][m], rt, "episode return", atol=1e-9)
     sg = b.stats()
-    for k, name in enumerate(("episodes", "return_sum", "return_sq_sum", "length_sum", "nonfinite_steps",
+    for k, name in enumerate(("episodes", "return_sum", "return_sq_sum", "length_sum", "nonfinite_events",
                               "terminated", "truncated")):
         assert np.isclose(sg[name], o.stats[k], rtol=1e-6, atol=1e-9), (name, sg[name], o.stats[k])
     assert sg["episodes"] >= 3 * n
@@ -279,3 +279,25 @@ def test_maximum_size_8M_envs_slab_invariance():
         assert torch.equal(s.state[:3, :m], ref_state[:, r * m:(r + 1) * m])
         assert torch.equal(s.ep_return[:m], ref_ret[r * m:(r + 1) * m])
         s.close()
+
+
+def test_divergence_events_are_counted_once(oracle_api):
+    """+-500 impulse actions blow dynamic.py's Lorenz up: NaN/inf propagate silently as
+    in the reference; stats[4] counts each env's finite -> non-finite transition exactly once."""
+    import torch
+    O = oracle_api
+    n, T = 4096, 400
+    b = H.gpu_batch("lorenz3", n, seed=3, autoreset=True, max_episode_steps=0)
+    o = O.Oracle("lorenz3", n, flags=O.F_AUTORESET, seed=3)
+    b.reset(); o.reset()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    acts = ((torch.rand((T, n, 3), generator=g) * 2 - 1) * 500).to(b.device)
+    b.rollout(T, acts, want=("reward",))
+    ao = np.ascontiguousarray(np.pad(acts.cpu().numpy().transpose(0, 2, 1), ((0, 0), (0, 0), (0, o.n_pad - n))))
+    with np.errstate(all="ignore"):
+        o.rollout(T, ao)
+    st = b.stats()
+    nonfinite_now = int((~torch.isfinite(b.state[:3, :n]).all(0)).sum().item())
+    assert st["nonfinite_events"] == o.stats[4] == nonfinite_now > 0
+    assert H.same_nonfinite(b.state.cpu().numpy()[:3, :n], o.state[:3, :n])
+    b.close()
