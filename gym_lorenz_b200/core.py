@@ -97,6 +97,14 @@ class ChaosBatch:
         L.check(self.lib.cl_create(C.byref(self.cfg), C.byref(ctx)), None, "cl_create")
         self.ctx = ctx
         self._host_views = None
+        # cached per-call objects of the hot `step()` path (views alias the static planes)
+        N = self.num_envs
+        self._obs_view = self._view(self.obs_planes)
+        self._rew_view = self.reward_buf[:N]
+        self._done_view = self.done_buf[:N]
+        self._io_step = self._io()
+        self._bufs_ref = C.byref(self._bufs)
+        self._io_step_ref = C.byref(self._io_step)
         L.check(self.lib.cl_init_persistent(self.ctx, self._stream(), C.byref(self._bufs)),
                 self.ctx, "cl_init_persistent")
 
@@ -193,12 +201,17 @@ class ChaosBatch:
         observation is in `terminal_obs()`, SB3 DummyVecEnv.step_wait style.
         `noise` (f64 [noise_dim, n_pad] standard normals) overrides the Philox process noise.
         """
-        actions = self._check_action(actions)
-        io = self._io(action=actions, noise=noise)
-        L.check(self.lib.cl_step(self.ctx, self._stream(), C.byref(self._bufs), C.byref(io)),
-                self.ctx, "cl_step")
-        N = self.num_envs
-        return self._view(self.obs_planes), self.reward_buf[:N], self.done_buf[:N]
+        if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.float32 and actions.device == self.device
+                and actions.dim() == 2 and actions.shape[0] == self.num_envs and actions.shape[1] == self.act_dim):
+            actions = self._check_action(actions)
+        io = self._io_step
+        io.action, io.act_es, io.act_cs = actions.data_ptr(), actions.stride(0), actions.stride(1)
+        io.noise = None if noise is None else noise.data_ptr()
+        rc = self.lib.cl_step(self.ctx, self._stream(), self._bufs_ref, self._io_step_ref)
+        if rc != 0:
+            L.check(rc, self.ctx, "cl_step")
+        self._keep_step = (actions, noise)
+        return self._obs_view, self._rew_view, self._done_view
 
     def terminal_obs(self) -> torch.Tensor:
         return self._view(self.term_obs_planes)
