@@ -85,3 +85,26 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "chaos_oracle" not in text, f
                 assert "ref_loader" not in text, f
+
+
+def test_compat_package_has_the_reference_import_names():
+    """`import gym_lorenz` / `from gym_lorenz.envs import HRSyncEnv, PMSM_Sync_Env` resolve to the
+    GPU facades (reference: gym_lorenz/__init__.py:4-23, envs/__init__.py:2-3)."""
+    import importlib
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "compat"))
+    try:
+        for m in [k for k in sys.modules if k == "gym_lorenz" or k.startswith("gym_lorenz.")]:
+            del sys.modules[m]
+        pkg = importlib.import_module("gym_lorenz")
+        envs = importlib.import_module("gym_lorenz.envs")
+        assert hasattr(envs, "HRSyncEnv") and hasattr(envs, "PMSM_Sync_Env")
+        assert envs.HRSyncEnv.__module__ == "gym_lorenz_b200.envs"
+        assert pkg.REGISTERED in (True, False)
+        import inspect
+        assert list(inspect.signature(envs.HRSyncEnv.__init__).parameters)[1:4] == ["add_noise", "eval_mode", "add_filter"]
+        assert list(inspect.signature(envs.PMSM_Sync_Env.__init__).parameters)[1:3] == ["alpha", "add_noise"]
+    finally:
+        sys.path.remove(os.path.join(ROOT, "compat"))
+        for m in [k for k in sys.modules if k == "gym_lorenz" or k.startswith("gym_lorenz.")]:
+            del sys.modules[m]
