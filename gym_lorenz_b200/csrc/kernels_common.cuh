@@ -290,8 +290,9 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
   const bool want_noise = E::NOISE > 0 && E::uses_noise(p);
   const int T = ROLL ? p.T : 1;
 
-  // actions are fetched one control interval ahead so that their HBM latency can hide behind
-  // the previous interval's integration (only ~3.5 warps per scheduler at 65,536 envs)
+  // actions are fetched one control interval ahead; this only hides their latency while
+  // scoreboard slots are free (ptxas drains the loads before long bodies) --
+  // the dynamic kernel below stages them through shared memory instead
   float a_next[E::ACT];
 #pragma unroll
   for (int c = 0; c < E::ACT; ++c)

@@ -201,3 +201,41 @@ def test_dynamic_rollout_many_handoffs_stress(kind, monkeypatch):
             for x, y in zip(ref, cur):
                 assert torch.equal(torch.nan_to_num(x.double()), torch.nan_to_num(y.double())), (kind, rep)
         b.close()
+
+
+def test_pmsm_rk4_with_parameter_jitter_vs_oracle_and_scipy(oracle_api):
+    """BASELINE configs[2]: chaotic PMSM pair, 65,536 envs, FP64, per-env sigma/gamma ~ U(0.9,1.1) x
+    nominal.  Per control interval vs the oracle (1e-12) and, for a sample, vs DOP853 (1e-9)."""
+    import torch
+    from scipy.integrate import solve_ivp
+    O = oracle_api
+    n = 65536
+    b = H.gpu_batch("pmsm_rk4", n, seed=17, param_jitter=0.1, substeps=4, autoreset=False, max_episode_steps=0)
+    o = O.Oracle("pmsm_rk4", n, seed=17, param_jitter=0.1, substeps=4, dt=0.001, act_limit=1.0, act_gain=50.0, alpha=0.5)
+    b.reset(); o.reset()
+    assert np.array_equal(b.state.cpu().numpy(), o.state)
+    rng = np.random.default_rng(2)
+    for t in range(3):
+        o.state[...] = b.state.cpu().numpy()
+        pre = o.state.copy()
+        a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        obs, rew, done = b.step(torch.as_tensor(a, device=b.device))
+        oo, ro, do, _ = o.step(np.ascontiguousarray(a.T))
+        H.assert_close(b.state.cpu().numpy()[:6], o.state[:6], 1e-12, "pmsm_rk4 state", atol=1e-13)
+        H.assert_close(rew.cpu().numpy(), ro, 1e-12, "pmsm_rk4 reward", atol=1e-12)
+        assert np.array_equal(done.cpu().numpy(), do)
+    got = b.state.cpu().numpy()
+
+    def f(_t, s, u, q):
+        x, y, z = s
+        return [-x + y * z + u[0], -y - x * z + q[1] * z + u[1], q[0] * (y - z)]
+    worst = 0.0
+    for i in range(0, n, n // 16):
+        q = pre[6:8, i]
+        u = (float(a[i, 0]) * 50.0, float(a[i, 1]) * 50.0)
+        r1 = solve_ivp(f, (0, 0.001), pre[0:3, i], args=((0.0, 0.0), q), method="DOP853", rtol=1e-13, atol=1e-13).y[:, -1]
+        r2 = solve_ivp(f, (0, 0.001), pre[3:6, i], args=(u, q), method="DOP853", rtol=1e-13, atol=1e-13).y[:, -1]
+        worst = max(worst, float(np.max(np.abs(got[0:3, i] - r1) / np.maximum(np.abs(r1), 1.0))),
+                    float(np.max(np.abs(got[3:6, i] - r2) / np.maximum(np.abs(r2), 1.0))))
+    assert worst < 1e-9, worst
+    b.close()
