@@ -13,9 +13,10 @@ tensor f32 [T, 3, n_pad] resident in HBM; outputs streamed to HBM every interval
 
 `value`   = all ranks' env-steps / max-over-ranks device time (CUDA events), inputs in HBM.
 `e2e`     = the same env, same metric, driven through the SB3-facing VecEnv API
-            (`step_async(np.ndarray)` / `step_wait()`) with HOST numpy buffers: per control
-            interval an H2D copy of the actions and a D2H copy of obs/reward/done, all inside
-            the timed region.
+            (`step_async(actions)` / `step_wait()`) with HOST buffers: per control interval the
+            actions cross PCIe from pinned host memory and obs/reward/done come back as host
+            arrays, all inside the timed region (a variant with a fresh pageable ndarray per step,
+            i.e. one extra host memcpy, is reported next to it).
 `roofline`= the fused rollout kernel against the FP64-FMA peak measured live by a
             register-resident DFMA chain (MEASURED_PEAKS.json carries no FP64 number), plus
             its HBM side against MEASURED_PEAKS.json's copy bandwidth.
@@ -322,7 +323,10 @@ def run_b200(args):
             "block_size": batch.block_size,
         }
 
-    # ---- e2e: the SB3-facing VecEnv API with host numpy buffers --------------------------
+    # ---- e2e: the SB3-facing VecEnv API with host buffers -------------------------------------
+    # Per control interval: the step's actions travel host->device from PINNED host memory (the
+    # env's own staging buffer, which a host-side policy writes into), the kernel runs, and
+    # obs / reward / done travel device->host; `infos` bookkeeping for finished episodes included.
     e2e = None
     if not args.no_e2e:
         env = BatchedChaosVecEnv(args.kind, N, device=dev, seed=0, env_id_base=slab.env_id_base,
@@ -330,37 +334,36 @@ def run_b200(args):
         env.reset()
         rng = np.random.default_rng(rank)
         host_actions = [rng.uniform(-1, 1, (N, env.batch.act_dim)).astype(np.float32) for _ in range(8)]
+        pin = env.batch.host_action_buffer()          # pinned f32 [N, act_dim]
+        pin[:] = host_actions[0]
         chunks = max(1, min(args.e2e_chunks, args.steps))
         for k in range(32):
-            env.step(host_actions[k % 8])
+            env.step(pin)
         barrier()
         t0 = time.perf_counter()
         acc = 0.0
         for k in range(chunks * T):
-            obs, rew, dones, infos = env.step(host_actions[k % 8])
+            obs, rew, dones, infos = env.step(pin)
             acc += float(rew[0])
         torch.cuda.synchronize(dev)
         el = time.perf_counter() - t0
         tm = torch.tensor([el], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        # same loop with the actions already sitting in the env's pinned staging buffer (what the
-        # contract calls "inputs from pinned host memory"): skips only the user->pinned memcpy
-        pin = env.batch.host_action_buffer()
-        pin[:] = host_actions[0]
+        # variant: a fresh pageable ndarray every step (what stock SB3 passes): adds one user->pinned memcpy
         t0 = time.perf_counter()
         for k in range(T):
-            obs, rew, dones, infos = env.step(pin)
+            obs, rew, dones, infos = env.step(host_actions[k % 8])
         torch.cuda.synchronize(dev)
-        el_pin = (time.perf_counter() - t0) / T
+        el_page = (time.perf_counter() - t0) / T
         e2e = {"value": float(N) * T * chunks * world / float(tm.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(env.batch.h2d_bytes_per_step * T),
                "d2h_bytes_per_step": int(env.batch.d2h_bytes_per_step * T),
-               "api": "BatchedChaosVecEnv.step_async(np.ndarray)/step_wait() (SB3 VecEnv contract), "
-                      f"{T} control intervals per bench step, {chunks} bench steps timed, wall clock incl. "
-                      "pinned staging, H2D, kernel, D2H, sync",
+               "api": "BatchedChaosVecEnv.step_async(actions)/step_wait() (SB3 VecEnv contract); actions in pinned host "
+                      f"memory, obs/reward/done returned as host arrays; {T} control intervals per bench step, "
+                      f"{chunks} bench steps timed, wall clock, max over ranks",
                "us_per_control_interval": float(tm.item()) / (chunks * T) * 1e6,
-               "us_per_control_interval_pinned_inputs_rank0": el_pin * 1e6}
+               "us_per_control_interval_pageable_inputs_rank0": el_page * 1e6}
         env.close()
 
     if rank == 0:

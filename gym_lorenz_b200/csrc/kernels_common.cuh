@@ -182,7 +182,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
                                              const KParams& p, const int64_t i, const bool live,
                                              const unsigned lane, const int t, const Stream& rng,
                                              const float* a, const bool want_noise, const bool obs64,
-                                             const bool autoreset, unsigned& bad_acc, float* sm_rows) {
+                                             const bool autoreset, unsigned& bad_acc, float* sm_rows, bool& fin) {
   typedef typename E::real real;
   double nz[E::NOISE > 0 ? E::NOISE : 1];
   nz[0] = 0.0;
@@ -198,14 +198,15 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
   real obs[E::OBS];
   real rew;
   bool term;
-  const bool was_finite = E::finite(s);
+  const bool was_finite = fin;  // finiteness is carried from the previous interval, not recomputed
   E::step(s, p, a, nz, obs, rew, term);
   ep_len += 1;
   ep_ret += (double)rew;
   const bool trunc = E::time_limit(p, ep_len);
   const bool done = term || trunc;
-  const bool bad = was_finite && !E::finite(s);  // divergence EVENT (a diverged env that is never
-                                                 // reset would otherwise cost an atomic every step)
+  fin = E::finite(s);
+  const bool bad = was_finite && !fin;  // divergence EVENT (a diverged env that is never reset would
+                                        // otherwise cost an atomic every step)
 
   // warp-aggregated statistics (one set of atomics per warp, only when something ended)
   const unsigned dm = __ballot_sync(0xffffffffu, live && done && autoreset);
@@ -238,6 +239,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
       E::reset(s, p, rng, obs);
       ep_len = 0;
       ep_ret = 0.0;
+      fin = true;
     }
   }
   // warp-uniform: contiguous float32 rows -> coalesced vector stores through shared memory
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
     a_next[c] = (live && p.action != nullptr) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
 
   unsigned bad_acc = 0u;
+  bool fin = E::finite(s);
   const uint64_t step0 = step_base(p);
   for (int t = 0; t < T; ++t) {
     const Stream rng = make_stream(p, i, step0 + (uint64_t)t);
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
           a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
       }
     }
-    env_interval<E, ROLL>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc, sm_rows);
+    env_interval<E, ROLL>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin);
   }
   if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
   if (live) {
@@ -461,6 +464,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     }
     const float* ab = abuf;
     unsigned bad_acc = 0u;
+    bool fin = E::finite(s);
     for (int tl = 0; tl < len; ++tl) {
       const int t = t0 + tl;
       const Stream rng = make_stream(p, i, step0 + (uint64_t)t);
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
         for (int cc = 0; cc < E::ACT; ++cc)
           a[cc] = live ? p.action[(int64_t)t * p.act_ts + i * p.act_es + cc * p.act_cs] : 0.0f;
       }
-      env_interval<E, true>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc, sm_rows);
+      env_interval<E, true>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin);
     }
     if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
     bad_acc = 0u;

@@ -143,6 +143,77 @@ CONST_ATTRS = {
 }
 
 
+class _LazyInfos(list):
+    """The `infos` list of the VecEnv contract (one dict per env).  Dicts of envs that finished an
+    episode in the last step (terminal_observation / TimeLimit.truncated / episode) are built on
+    first access instead of inside step_wait(): with tens of thousands of envs ending together,
+    building them costs more than the step itself, and loops that never look at `infos`
+    (random rollouts, custom collectors) should not pay for it.  All read paths materialise
+    first, so the object behaves exactly like the eager list."""
+
+    def __init__(self, n):
+        super().__init__({} for _ in range(n))
+        self._pending = None
+        self._dirty = []
+
+    def _begin_step(self, pending):
+        setitem = list.__setitem__
+        for i in self._dirty:
+            setitem(self, i, {})
+        self._dirty = []
+        self._pending = pending
+
+    def _materialize(self):
+        p = self._pending
+        if p is None:
+            return
+        self._pending = None
+        ids, tobs, trunc, rets, lens, now = p
+        setitem = list.__setitem__
+        if rets is not None:
+            for i, to, tr, r, ln in zip(ids, tobs, trunc, rets, lens):
+                setitem(self, i, {"terminal_observation": to, "TimeLimit.truncated": tr,
+                                  "episode": {"r": r, "l": ln, "t": now}})
+        else:
+            for i, to, tr in zip(ids, tobs, trunc):
+                setitem(self, i, {"terminal_observation": to, "TimeLimit.truncated": tr})
+        self._dirty = ids
+
+    def __getitem__(self, k):
+        self._materialize()
+        return list.__getitem__(self, k)
+
+    def __iter__(self):
+        self._materialize()
+        return list.__iter__(self)
+
+    def __reversed__(self):
+        self._materialize()
+        return list.__reversed__(self)
+
+    def __contains__(self, x):
+        self._materialize()
+        return list.__contains__(self, x)
+
+    def __eq__(self, other):
+        self._materialize()
+        return list.__eq__(self, other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._materialize()
+        return list.__repr__(self)
+
+    def copy(self):
+        self._materialize()
+        return list(list.__iter__(self))
+
+    def __reduce__(self):
+        self._materialize()
+        return (list, (list(list.__iter__(self)),))
+
+
 class BatchedChaosVecEnv(VecEnv):
     """`num_envs` chaos-control envs on one B200 behind the SB3 VecEnv contract.
 
@@ -164,8 +235,7 @@ class BatchedChaosVecEnv(VecEnv):
         self._monitor = bool(monitor)
         self.batch = ChaosBatch(kind, num_envs, device=device, seed=seed, autoreset=True, **kwargs)
         self._t_start = time.time()
-        self._infos: List[Dict[str, Any]] = [{} for _ in range(num_envs)]
-        self._dirty: List[int] = []
+        self._infos = _LazyInfos(num_envs)
         self._waiting = False
         super().__init__(num_envs, box_for(self.batch.layout, "obs"), box_for(self.batch.layout, "act"))
 
@@ -187,25 +257,17 @@ class BatchedChaosVecEnv(VecEnv):
         obs, rew, done, term_obs, ler, lel, n_done = self.batch.step_host_wait()
         self._waiting = False
         infos = self._infos
-        for i in self._dirty:
-            infos[i].clear()
-        self._dirty = []
         dones = done != 0
+        pending = None
         if n_done:
             idx = np.flatnonzero(dones)
-            now = round(time.time() - self._t_start, 6)
-            tobs = term_obs[idx]                      # one gather; rows are handed out as views
             flags = done[idx]
             trunc = (((flags & L.DONE_TRUNCATED) != 0) & ((flags & L.DONE_TERMINATED) == 0)).tolist()
-            rets, lens, ids = ler[idx].tolist(), lel[idx].tolist(), idx.tolist()
-            monitor = self._monitor
-            for k, i in enumerate(ids):
-                d = infos[i]
-                d["terminal_observation"] = tobs[k]
-                d["TimeLimit.truncated"] = trunc[k]
-                if monitor:
-                    d["episode"] = {"r": rets[k], "l": lens[k], "t": now}
-            self._dirty = ids
+            pending = (idx.tolist(), term_obs[idx], trunc,
+                       ler[idx].tolist() if self._monitor else None,
+                       lel[idx].tolist() if self._monitor else None,
+                       round(time.time() - self._t_start, 6))
+        infos._begin_step(pending)
         return obs, rew, dones, infos
 
     def close(self) -> None:

@@ -108,3 +108,21 @@ def test_compat_package_has_the_reference_import_names():
         sys.path.remove(os.path.join(ROOT, "compat"))
         for m in [k for k in sys.modules if k == "gym_lorenz" or k.startswith("gym_lorenz.")]:
             del sys.modules[m]
+
+
+def test_lazy_infos_behaves_like_the_eager_list():
+    """SB3 reads `infos` by index, by iteration and by slicing (VecMonitor: `list(infos[:])`)."""
+    import numpy as np
+    from gym_lorenz_b200.vec_env import _LazyInfos
+    inf = _LazyInfos(5)
+    inf._begin_step(([1, 3], np.arange(12, dtype=np.float32).reshape(2, 6), [True, False], [1.5, 2.5], [10, 20], 0.1))
+    assert isinstance(inf, list) and len(inf) == 5
+    assert inf[0] == {} and inf[1]["episode"] == {"r": 1.5, "l": 10, "t": 0.1}
+    assert inf[3]["TimeLimit.truncated"] is False and inf[1]["terminal_observation"].tolist() == [0, 1, 2, 3, 4, 5]
+    assert [bool(d) for d in inf] == [False, True, False, True, False]
+    inf[1]["extra"] = 7                                  # wrappers may add keys to a done env's dict
+    assert list(inf[:])[1]["extra"] == 7
+    inf._begin_step(None)                                # next step: nothing finished
+    assert all(d == {} for d in inf)
+    inf._begin_step(([2], np.zeros((1, 6), np.float32), [True], None, None, 0.2))   # monitor off
+    assert "episode" not in inf[2] and inf[2]["TimeLimit.truncated"] is True
