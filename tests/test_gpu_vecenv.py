@@ -162,3 +162,50 @@ def test_reset_distribution_and_mask():
     assert torch.equal(after[:, 1:n:2], before[:, 1:n:2])
     assert not torch.equal(after[:3, 0:n:2], before[:3, 0:n:2])
     b.close()
+
+
+@pytest.mark.parametrize("kind", ["lorenz3", "hr_sync", "pmsm_sync", "lorenz_rk4"])
+def test_graph_mode_replay_equals_eager_stepping(kind):
+    """cl_set_graph_mode: the Philox step index lives on the device, so a captured sequence of
+    step launches can be replayed and still advances the random streams (auto-resets, noise)."""
+    import torch
+    n, per_graph, replays = 3000, 6, 4
+    kw = dict(seed=31, autoreset=True, max_episode_steps=5)
+    if kind in ("hr_sync", "pmsm_sync"):
+        kw["add_noise"] = True
+    amp = 0.05 if kind == "lorenz3" else 1.0
+    g0 = torch.Generator(device="cpu").manual_seed(2)
+    acts = ((torch.rand((per_graph, n, H.gpu_batch(kind, 1).act_dim), generator=g0) * 2 - 1) * amp).to("cuda:0")
+    # eager reference: per_graph * replays steps, cycling through the same action tensors
+    e = H.gpu_batch(kind, n, **kw)
+    e.reset()
+    for r in range(replays):
+        for t in range(per_graph):
+            e.step(acts[t])
+    torch.cuda.synchronize()
+    # graph: capture per_graph steps once, replay
+    b = H.gpu_batch(kind, n, **kw)
+    b.reset()
+    b.set_graph_mode(True)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):          # warm-up outside capture (does not advance: we restore below)
+        sd = b.state_dict()
+        b.step(acts[0])
+        b.load_state_dict(sd)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for t in range(per_graph):
+            b.step(acts[t])
+    for r in range(replays):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert b.step_index == e.step_index == 1 + per_graph * replays
+    assert torch.equal(torch.nan_to_num(b.state), torch.nan_to_num(e.state))
+    assert torch.equal(b.ep_len, e.ep_len) and torch.equal(b.ep_return, e.ep_return)
+    assert b.stats()["episodes"] == e.stats()["episodes"] > 0
+    b.set_graph_mode(False)
+    assert b.step_index == e.step_index
+    b.close(); e.close()
