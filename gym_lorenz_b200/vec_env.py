@@ -173,7 +173,7 @@ class _LazyInfos(list):
         if rets is not None:
             for i, to, tr, r, ln in zip(ids, tobs, trunc, rets, lens):
                 setitem(self, i, {"terminal_observation": to, "TimeLimit.truncated": tr,
-                                  "episode": {"r": r, "l": ln, "t": now}})
+                                  "episode": {"r": round(r, 6), "l": ln, "t": now}})  # SB3 Monitor rounds r
         else:
             for i, to, tr in zip(ids, tobs, trunc):
                 setitem(self, i, {"terminal_observation": to, "TimeLimit.truncated": tr})
