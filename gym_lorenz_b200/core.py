@@ -217,21 +217,28 @@ class ChaosBatch:
         return self._view(self.term_obs_planes)
 
     def rollout(self, T: int, actions: Optional[torch.Tensor] = None, *, synth_amp: Optional[float] = None,
-                out: Optional[Dict[str, torch.Tensor]] = None, want=("obs", "reward", "done")):
+                out: Optional[Dict[str, torch.Tensor]] = None, want=("obs", "reward", "done"),
+                obs_layout: str = "planes"):
         """T fused control intervals in ONE launch (state stays in registers).
 
         actions: f32 [T, N, act_dim] (any strides) or None -> in-kernel Philox
-        U(-synth_amp, synth_amp) (default: the action-space bound).  Outputs are time-major
-        SoA buffers: obs [T, obs_dim, n_pad], reward [T, n_pad], done [T, n_pad]; pass `out`
-        to reuse buffers, `want` to skip streams.
+        U(-synth_amp, synth_amp) (default: the action-space bound).  Outputs are time-major:
+        reward [T, n_pad], done [T, n_pad] and obs either as SoA planes [T, obs_dim, n_pad]
+        (`obs_layout="planes"`) or as policy-shaped rows [T, N, obs_dim] (`obs_layout="rows"`,
+        float32 only; written with warp-transposed 16-byte stores).  Pass `out` to reuse buffers,
+        `want` to skip streams.
         """
         T = int(T)
         dev, NP = self.device, self.n_pad
         if out is None:
             out = {}
+        rows = obs_layout == "rows"
+        if rows and self.obs_f64:
+            raise ValueError("obs_layout='rows' is float32 only")
         odt = torch.float64 if self.obs_f64 else torch.float32
         if "obs" in want and "obs" not in out:
-            out["obs"] = torch.empty((T, self.obs_dim, NP), dtype=odt, device=dev)
+            shape = (T, self.num_envs, self.obs_dim) if rows else (T, self.obs_dim, NP)
+            out["obs"] = torch.empty(shape, dtype=odt, device=dev)
         if "reward" in want and "reward" not in out:
             out["reward"] = torch.empty((T, NP), dtype=self.real, device=dev)
         if "done" in want and "done" not in out:
@@ -245,7 +252,13 @@ class ChaosBatch:
             io.action, desc.act_ts, io.act_es, io.act_cs = _ptr(actions), actions.stride(0), \
                 actions.stride(1), actions.stride(2)
         if "obs" in want:
-            io.obs, io.obs_es, io.obs_cs, desc.obs_ts = _ptr(out["obs"]), 1, NP, self.obs_dim * NP
+            o = out["obs"]
+            if rows:
+                if tuple(o.shape) != (T, self.num_envs, self.obs_dim) or not o.is_contiguous():
+                    raise ValueError("obs buffer must be contiguous [T, N, obs_dim] for obs_layout='rows'")
+                io.obs, io.obs_es, io.obs_cs, desc.obs_ts = _ptr(o), self.obs_dim, 1, self.num_envs * self.obs_dim
+            else:
+                io.obs, io.obs_es, io.obs_cs, desc.obs_ts = _ptr(o), 1, NP, self.obs_dim * NP
         if "reward" in want:
             io.reward, desc.rew_ts = _ptr(out["reward"]), NP
         if "done" in want:

@@ -62,6 +62,8 @@ struct KParams {
   uint32_t* dyn_counter;
   uint32_t* dyn_progress;
   int32_t dyn_chunk, dyn_nchunks, dyn_nwarps, dyn_tma, dyn_grid;
+  // observations go out as contiguous, 16-byte aligned float32 rows -> warp-transposed vector stores
+  int32_t rows_fast;
 };
 
 enum LaunchMode { MODE_STEP = 0, MODE_ROLLOUT = 1, MODE_RESET = 2, MODE_INIT = 3, MODE_ROLLOUT_DYN = 4 };
@@ -243,7 +245,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
     }
   }
   // warp-uniform: contiguous float32 rows -> coalesced vector stores through shared memory
-  const bool rows_fast = p.obs != nullptr && !obs64 && p.obs_cs == 1 && p.obs_es == E::OBS;
+  const bool rows_fast = p.rows_fast != 0;
   if (rows_fast)
     store_obs_rows_warp<real, E::OBS>(sm_rows, (float*)p.obs + oo, i - (int64_t)lane, p.n, lane, obs);
   if (live) {
@@ -525,19 +527,25 @@ __global__ void __launch_bounds__(256) k_init(const KParams p) {
   p.ep_return[i] = 0.0;
 }
 
+// Row-store fast path: contiguous float32 rows [N][OBS] whose every warp segment is 16-byte
+// aligned (base pointer, and in rollouts the per-interval stride).  Decided once on the host.
 template <class E>
-inline size_t row_smem(const KParams& p, int block) {
-  const bool rows = p.obs != nullptr && !(p.flags & CL_F_OBS_F64) && p.obs_cs == 1 && p.obs_es == E::OBS;
-  return rows ? (size_t)(block / 32) * 32 * E::OBS * sizeof(float) : 0;
+inline bool rows_fast_ok(const KParams& p, bool rollout) {
+  return p.obs != nullptr && !(p.flags & CL_F_OBS_F64) && p.obs_cs == 1 && p.obs_es == E::OBS &&
+         ((uintptr_t)p.obs % 16) == 0 && (!rollout || (p.obs_ts % 4) == 0);
 }
 
 template <class E>
-cudaError_t launch_env(const KParams& p, int mode, cudaStream_t st, int block) {
+cudaError_t launch_env(const KParams& p_in, int mode, cudaStream_t st, int block) {
+  KParams p = p_in;
+  const bool roll = (mode == MODE_ROLLOUT || mode == MODE_ROLLOUT_DYN);
+  p.rows_fast = (mode == MODE_STEP || roll) && rows_fast_ok<E>(p, roll) ? 1 : 0;
+  const size_t row_smem = p.rows_fast ? (size_t)(block / 32) * 32 * E::OBS * sizeof(float) : 0;
   const unsigned grid = (unsigned)((p.n + block - 1) / block);
   switch (mode) {
     // dynamic smem only when observations go out as contiguous float32 rows (row-store staging)
-    case MODE_STEP: k_step<E, false><<<grid, block, row_smem<E>(p, block), st>>>(p); break;
-    case MODE_ROLLOUT: k_step<E, true><<<grid, block, row_smem<E>(p, block), st>>>(p); break;
+    case MODE_STEP: k_step<E, false><<<grid, block, row_smem, st>>>(p); break;
+    case MODE_ROLLOUT: k_step<E, true><<<grid, block, row_smem, st>>>(p); break;
     case MODE_RESET: k_reset<E><<<grid, block, 0, st>>>(p); break;
     case MODE_INIT: k_init<E><<<grid, block, 0, st>>>(p); break;
     case MODE_ROLLOUT_DYN: {

@@ -239,3 +239,25 @@ def test_pmsm_rk4_with_parameter_jitter_vs_oracle_and_scipy(oracle_api):
                     float(np.max(np.abs(got[3:6, i] - r2) / np.maximum(np.abs(r2), 1.0))))
     assert worst < 1e-9, worst
     b.close()
+
+
+@pytest.mark.parametrize("kind,n", [("lorenz_rk4", 65536), ("hr_sync", 4096), ("lorenz3", 33), ("pmsm_sync", 1001)])
+def test_row_major_observation_rollout_equals_plane_layout(kind, n, monkeypatch):
+    """obs_layout='rows' ([T, N, obs_dim], warp-transposed 16-byte stores when every row block is
+    16-byte aligned, generic stores otherwise -- n=33 and n=1001 make the per-interval stride
+    unaligned) must carry exactly the values of the SoA plane layout, static and dynamic kernel."""
+    import torch
+    T = 9
+    for dyn in ("0", "1"):
+        monkeypatch.setenv("CHAOS_B200_DYN", dyn)
+        outs = []
+        for layout in ("planes", "rows"):
+            b = H.gpu_batch(kind, n, seed=3, max_episode_steps=4)
+            b.reset()
+            o = b.rollout(T, None, obs_layout=layout)
+            torch.cuda.synchronize()
+            outs.append(o["obs"].clone())
+            b.close()
+        planes, rows = outs
+        assert rows.shape == (T, n, planes.shape[1])
+        assert torch.equal(torch.nan_to_num(planes[:, :, :n].permute(0, 2, 1)), torch.nan_to_num(rows))
