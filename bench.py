@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="bench steps timed on the host-buffer path")
+    ap.add_argument("--stats-every", type=int, default=16,
+                    help="N>1: all-reduce the 64 B episode-statistics vector every this many bench steps")
     return ap.parse_args()
 
 
@@ -72,7 +74,8 @@ def workload_config(args, world):
         if args.kind == "lorenz_rk4" else f"{args.kind} (RK4 x {args.substeps}), {args.envs_per_gpu} envs/GPU, random actions",
         "kind": args.kind, "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
         "substeps": args.substeps, "control_intervals_per_step": args.chunk,
-        "parallelism": f"env-slab x{world} (no data-path collective; 64 B stats all-reduce per step)",
+        "parallelism": f"env-slab x{world} (no data-path collective; 64 B NCCL stats all-reduce every "
+                       f"{args.stats_every} steps on a side stream)",
         "l2": "per-step action/obs/reward streams (>=750 MB) exceed the 126 MB L2; env state "
               "(3 MB) lives in registers across the whole launch",
     }
@@ -224,9 +227,13 @@ def run_b200(args):
            "done": torch.empty((T, NP), dtype=torch.uint8, device=dev)}
     side = torch.cuda.Stream(device=dev)
 
+    step_no = [0]
+
     def one_step():
         batch.rollout(T, actions, out=out)
-        if world > 1:   # episode-statistics all-reduce on a side stream, off the critical path
+        step_no[0] += 1
+        if world > 1 and step_no[0] % args.stats_every == 0:
+            # cumulative episode statistics, all-reduced on a side stream off the critical path
             st = batch.stats_tensor(clear=False)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
