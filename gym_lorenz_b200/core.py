@@ -96,7 +96,10 @@ class ChaosBatch:
         ctx = C.c_void_p()
         L.check(self.lib.cl_create(C.byref(self.cfg), C.byref(ctx)), None, "cl_create")
         self.ctx = ctx
-        self._host_views = None
+        self._host_views = {}
+        self._pin_view = None
+        self._host_view = L.HostView()
+        self._host_view_ref = C.byref(self._host_view)
         # cached per-call objects of the hot `step()` path (views alias the static planes)
         N = self.num_envs
         self._obs_view = self._view(self.obs_planes)
@@ -316,33 +319,39 @@ class ChaosBatch:
 
     def host_action_buffer(self) -> np.ndarray:
         """Pinned f32 [N, act_dim] staging area; write actions here to skip one host copy."""
-        p = C.c_void_p()
-        L.check(self.lib.cl_host_action_staging(self.ctx, C.byref(p)), self.ctx, "cl_host_action_staging")
-        arr = (C.c_float * (self.num_envs * self.act_dim)).from_address(p.value)
-        return np.ctypeslib.as_array(arr).reshape(self.num_envs, self.act_dim)
+        if self._pin_view is None:
+            p = C.c_void_p()
+            L.check(self.lib.cl_host_action_staging(self.ctx, C.byref(p)), self.ctx, "cl_host_action_staging")
+            arr = (C.c_float * (self.num_envs * self.act_dim)).from_address(p.value)
+            self._pin_view = np.ctypeslib.as_array(arr).reshape(self.num_envs, self.act_dim)
+        return self._pin_view
 
     def step_host_async(self, actions: Optional[np.ndarray]) -> None:
-        """SB3 step_async: f32 [N, act_dim] host actions -> H2D + kernel + D2H, enqueued."""
-        if actions is None:
+        """SB3 step_async: f32 [N, act_dim] host actions -> (H2D +) kernel (+ D2H), enqueued.
+        Passing the array returned by `host_action_buffer()` (or None after writing into it)
+        skips the user->pinned staging copy."""
+        if actions is None or actions is self._pin_view:
             ap = None
         else:
-            a = np.ascontiguousarray(actions, dtype=np.float32)
+            a = actions
+            if not (type(a) is np.ndarray and a.dtype == np.float32 and a.flags.c_contiguous):
+                a = np.ascontiguousarray(actions, dtype=np.float32)
             if a.shape != (self.num_envs, self.act_dim):
                 raise ValueError(f"actions must be [{self.num_envs}, {self.act_dim}], got {a.shape}")
-            ap = C.c_void_p(a.ctypes.data)
+            ap = a.__array_interface__["data"][0]
             self._keep_act = a
-        L.check(self.lib.cl_step_host_async(self.ctx, self._host_stream(), C.byref(self._bufs), ap),
-                self.ctx, "cl_step_host_async")
+        rc = self.lib.cl_step_host_async(self.ctx, self._host_stream(), self._bufs_ref, ap)
+        if rc != 0:
+            L.check(rc, self.ctx, "cl_step_host_async")
 
     def step_host_wait(self):
         """SB3 step_wait: blocks, returns zero-copy numpy views of the pinned result slot
         (valid for the next 2 steps): obs f32 [N, obs_dim], reward f32 [N], done u8 [N],
         term_obs, last_ep_ret, last_ep_len, n_done."""
-        v = L.HostView()
-        L.check(self.lib.cl_step_host_wait_view(self.ctx, self._host_stream(), C.byref(v)),
-                self.ctx, "cl_step_host_wait_view")
-        if self._host_views is None:
-            self._host_views = {}
+        v = self._host_view
+        rc = self.lib.cl_step_host_wait_view(self.ctx, self._host_stream(), self._host_view_ref)
+        if rc != 0:
+            L.check(rc, self.ctx, "cl_step_host_wait_view")
         key = v.obs
         views = self._host_views.get(key)
         if views is None:
@@ -356,7 +365,7 @@ class ChaosBatch:
                      arr(v.done, C.c_uint8, (N,)), arr(v.term_obs, C.c_float, (N, O)),
                      arr(v.last_ep_ret, C.c_double, (N,)), arr(v.last_ep_len, C.c_int32, (N,)))
             self._host_views[key] = views
-        return (*views, int(v.n_done))
+        return (*views, v.n_done)
 
     def reset_host(self) -> np.ndarray:
         obs = np.empty((self.num_envs, self.obs_dim), np.float32)
