@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libchaos_b200.so")
+# CHAOS_B200_LIB: tuning override (A/B runs of differently compiled builds, tools/ab_variants.sh)
+LIB_PATH = os.environ.get("CHAOS_B200_LIB") or os.path.join(HERE, "libchaos_b200.so")
 
 CL_ABI_VERSION = 1
 

@@ -126,9 +126,9 @@ struct EnvLorenzRK4 {
                               bool& term) {
     const float lim = p.act_limit_f;
     const R g = sizeof(R) == 8 ? (R)p.act_gain : (R)p.act_gain_f;
-    const R u1 = (R)clipf(a[0], -lim, lim) * g;
-    const R u2 = (R)clipf(a[1], -lim, lim) * g;
-    const R u3 = (R)clipf(a[2], -lim, lim) * g;
+    const R u1 = mul_keep((R)clipf(a[0], -lim, lim), g);
+    const R u2 = mul_keep((R)clipf(a[1], -lim, lim), g);
+    const R u3 = mul_keep((R)clipf(a[2], -lim, lim), g);
     if (sizeof(R) == 8) {
       if (s.uni) {
         const LorenzPar<R> qc = {(R)p.nom[0], (R)p.nom[1], (R)p.nom[2]};
@@ -234,8 +234,8 @@ struct EnvPMSMRK4 {
   __device__ static void step(S& s, const KParams& p, const float* a, const double*, double* obs,
                               double& rew, bool& term) {
     const float lim = (float)p.act_limit;
-    const double u1 = (double)clipf(a[0], -lim, lim) * p.act_gain;
-    const double u2 = (double)clipf(a[1], -lim, lim) * p.act_gain;
+    const double u1 = mul_keep((double)clipf(a[0], -lim, lim), p.act_gain);
+    const double u2 = mul_keep((double)clipf(a[1], -lim, lim), p.act_gain);
     if (s.uni) {
       const PMSMPar qc = {p.nom[0], p.nom[1]};
       pmsm_rk4(qc, s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);

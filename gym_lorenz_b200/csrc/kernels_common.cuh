@@ -88,6 +88,12 @@ __device__ __forceinline__ double pow_pos(double x, double a) {
   return exp(a * log(x));   // log(inf)=inf -> inf, NaN propagates, x<0 -> NaN like pow for non-integer a
 }
 
+// products that must stay products: `u = a*g; ... u - y` would otherwise be contracted into
+// fma(a, g, -y), a DFMA with three register sources (3 issue cycles instead of a 2-cycle DADD,
+// DESIGN.md "FP64 cost model") in every RK4 stage
+__device__ __forceinline__ double mul_keep(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_keep(float a, float b) { return __fmul_rn(a, b); }
+
 __device__ __forceinline__ Stream make_stream(const KParams& p, int64_t i, uint64_t step) {
   const uint64_t gid = (uint64_t)(p.env_id_base + i);
   Stream s;
