@@ -28,6 +28,7 @@ KIND_NAMES = {
 
 F_ADD_NOISE, F_EVAL_MODE, F_ADD_FILTER, F_AUTORESET, F_OBS_F64 = 0x01, 0x02, 0x04, 0x08, 0x10
 DONE_TERMINATED, DONE_TRUNCATED = 0x1, 0x2
+HOST_DMA, HOST_ZEROCOPY, HOST_PIPELINED = 0, 1, 2
 NSTATS = 8
 STAT_NAMES = ("episodes", "return_sum", "return_sq_sum", "length_sum", "nonfinite_events",
               "terminated", "truncated", "reserved")
@@ -108,6 +109,7 @@ SYMBOLS = [
     ("cl_set_graph_mode", C.c_int, [_VP, C.c_int]),
     ("cl_host_action_staging", C.c_int, [_VP, C.POINTER(_VP)]),
     ("cl_host_set_zero_copy", C.c_int, [_VP, C.c_int]),
+    ("cl_host_set_mode", C.c_int, [_VP, C.c_int, C.c_int]),
     ("cl_step_host_async", C.c_int, [_VP, _VP, C.POINTER(Buffers), _VP]),
     ("cl_step_host_wait", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_int64)]),
     ("cl_step_host_wait_view", C.c_int, [_VP, _VP, C.POINTER(HostView)]),

@@ -367,6 +367,12 @@ class ChaosBatch:
             self._host_views[key] = views
         return (*views, v.n_done)
 
+    def set_host_mode(self, mode: str, slices: int = 1) -> None:
+        """How `step_host_async` moves the data: "dma", "zerocopy" or "pipelined" (with `slices`
+        env slices alternating over two streams).  Results do not depend on it."""
+        m = {"dma": L.HOST_DMA, "zerocopy": L.HOST_ZEROCOPY, "pipelined": L.HOST_PIPELINED}[mode]
+        L.check(self.lib.cl_host_set_mode(self.ctx, m, int(slices)), self.ctx, "cl_host_set_mode")
+
     def reset_host(self) -> np.ndarray:
         obs = np.empty((self.num_envs, self.obs_dim), np.float32)
         L.check(self.lib.cl_reset_host(self.ctx, self._host_stream(), C.byref(self._bufs),

@@ -60,7 +60,16 @@ struct HostStage {
   int cur;        // slot being filled / last filled
   cudaStream_t stream;
   bool pending;
-  bool zero_copy;
+  // CL_HOST_DMA: H2D copy -> kernel -> one D2H copy.  CL_HOST_ZEROCOPY: the kernel reads the
+  // actions from and writes the results to pinned host memory.  CL_HOST_PIPELINED: the env batch
+  // is cut into slices that alternate over two streams; each slice's actions arrive by DMA
+  // (SM-initiated PCIe reads top out near 20 GB/s) and its kernel writes the results straight to
+  // pinned host memory, so slice j's upstream writes overlap slice j+1's downstream copy.
+  int mode;
+  bool extras_on_host;  // the pending step wrote term_obs / last_ep_* to the host slot itself
+  int slices;        // CL_HOST_PIPELINED: number of env slices (>= 1)
+  cudaStream_t side; // second stream of the pipeline
+  cudaEvent_t ev_fork, ev_join;
 };
 
 }  // namespace
@@ -206,6 +215,9 @@ static void host_stage_free(cl_ctx* ctx) {
     cudaFreeHost(h.slot[k].term_obs); cudaFreeHost(h.slot[k].last_ep_ret); cudaFreeHost(h.slot[k].last_ep_len);
   }
   cudaStreamDestroy(h.stream);
+  cudaStreamDestroy(h.side);
+  cudaEventDestroy(h.ev_fork);
+  cudaEventDestroy(h.ev_join);
   h.ready = false;
 }
 
@@ -464,9 +476,23 @@ static int host_stage_init(cl_ctx* ctx) {
   }
   h.cur = 0;
   h.pending = false;
-  // default: zero-copy (measured 135 vs 146 us per step at 65,536 envs, 30 vs 37 us at 4,096);
-  // CHAOS_B200_ZEROCOPY=0 selects the DMA-copy chain
-  h.zero_copy = !(getenv("CHAOS_B200_ZEROCOPY") != nullptr && getenv("CHAOS_B200_ZEROCOPY")[0] == '0');
+  CU(cudaStreamCreateWithFlags(&h.side, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&h.ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&h.ev_join, cudaEventDisableTiming));
+  // default: zero-copy (one launch, no copies: 23 / 73 us per step at 4,096 / 65,536 Lorenz envs
+  // vs 31 / 88 us for the DMA chain).  The sliced pipeline only pays when the caller's ndarray has
+  // to be staged at >= 262,144 envs: each slice costs ~9 us of host-side launch time
+  // (profiles/r01_e2e_host_modes.jsonl).  CHAOS_B200_HOST_MODE=dma|zerocopy|pipelined and
+  // CHAOS_B200_HOST_SLICES=k override (tuning); CHAOS_B200_ZEROCOPY=0 is the older spelling of dma.
+  h.slices = 1;
+  h.mode = CL_HOST_ZEROCOPY;
+  if (const char* ov = getenv("CHAOS_B200_ZEROCOPY")) { if (ov[0] == '0') h.mode = CL_HOST_DMA; }
+  if (const char* ov = getenv("CHAOS_B200_HOST_MODE")) {
+    if (!strcmp(ov, "dma")) h.mode = CL_HOST_DMA;
+    else if (!strcmp(ov, "zerocopy")) h.mode = CL_HOST_ZEROCOPY;
+    else if (!strcmp(ov, "pipelined")) { h.mode = CL_HOST_PIPELINED; if (h.slices < 2) h.slices = 2; }
+  }
+  if (const char* ov = getenv("CHAOS_B200_HOST_SLICES")) { const int k = atoi(ov); if (k >= 1 && k <= 64) h.slices = k; }
   h.ready = true;
   return CL_OK;
 }
@@ -493,39 +519,73 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
   const size_t N = (size_t)ctx->cfg.num_envs;
   const size_t A = (size_t)ctx->lay.act_dim, O = (size_t)ctx->lay.obs_dim;
   cudaStream_t st = host_stream(ctx, stream);
-  if (action_host && action_host != h.h_act) memcpy(h.h_act, action_host, N * A * sizeof(float));
+  const bool stage_copy = action_host && action_host != h.h_act;
   CU(cudaSetDevice(ctx->cfg.device));
-  // Zero-copy mode: the step kernel reads the actions from, and writes obs / reward / done to,
-  // the pinned host buffers directly (UVA-mapped), so both PCIe directions are driven by the SMs
-  // concurrently instead of a serial H2D -> kernel -> D2H chain of DMA copies.
-  const bool zc = h.zero_copy;
+  const int mode = (h.mode == CL_HOST_PIPELINED && ctx->graph_mode) ? CL_HOST_ZEROCOPY : h.mode;
+  const bool host_out = mode != CL_HOST_DMA;       // kernel writes obs / reward / done to pinned host memory
+  const bool host_in = mode == CL_HOST_ZEROCOPY;   // kernel reads the actions from pinned host memory
   h.cur = (h.cur + 1) % kHostRing;
   HostSlot& s = h.slot[h.cur];
-  if (!zc) CU(cudaMemcpyAsync(h.d_act, h.h_act, N * A * sizeof(float), cudaMemcpyHostToDevice, st));
   cl_io io;
   memset(&io, 0, sizeof(io));
-  io.action = zc ? h.h_act : h.d_act; io.act_es = (int64_t)A; io.act_cs = 1;
-  io.obs = zc ? s.obs : h.d_obs; io.obs_es = (int64_t)O; io.obs_cs = 1;
-  io.reward = zc ? s.reward : h.d_rew; io.done = zc ? s.done : h.d_done; io.term_obs = h.d_term;
-  io.last_ep_ret = h.d_ler; io.last_ep_len = h.d_lel;
+  io.action = host_in ? h.h_act : h.d_act; io.act_es = (int64_t)A; io.act_cs = 1;
+  io.obs = host_out ? s.obs : h.d_obs; io.obs_es = (int64_t)O; io.obs_cs = 1;
+  io.reward = host_out ? s.reward : h.d_rew; io.done = host_out ? s.done : h.d_done;
+  // finished episodes: terminal observation and Monitor numbers go straight to the host slot too
+  // (whole rows of the warps concerned), so a step that ends episodes needs no extra copies
+  io.term_obs = host_out ? s.term_obs : h.d_term;
+  io.last_ep_ret = host_out ? s.last_ep_ret : h.d_ler; io.last_ep_len = host_out ? s.last_ep_len : h.d_lel;
+  h.extras_on_host = host_out;
   KParams p;
   r = fill_params(ctx, buf, &io, p);
   if (r) return r;
   p.reward_f32 = 1;
   p.flags &= ~CL_F_OBS_F64;
-  r = launch(ctx, p, cl::MODE_STEP, st);
-  if (r) return r;
+  if (mode == CL_HOST_PIPELINED && h.slices > 1) {
+    // slice j runs on stream (j & 1): [DMA its actions in] -> [kernel: step, write results to host].
+    // The user's array is staged into pinned memory slice by slice too, so that host memcpy
+    // overlaps the device work of the slices already enqueued.
+    const size_t per = ((N + (size_t)h.slices - 1) / (size_t)h.slices + 255) / 256 * 256;  // whole blocks / warps
+    CU(cudaEventRecord(h.ev_fork, st));
+    CU(cudaStreamWaitEvent(h.side, h.ev_fork, 0));
+    int j = 0;
+    for (size_t b = 0; b < N; b += per, ++j) {
+      const size_t e = b + per < N ? b + per : N;
+      cudaStream_t sj = (j & 1) ? h.side : st;
+      if (stage_copy) memcpy(h.h_act + b * A, action_host + b * A, (e - b) * A * sizeof(float));
+      CU(cudaMemcpyAsync(h.d_act + b * A, h.h_act + b * A, (e - b) * A * sizeof(float), cudaMemcpyHostToDevice, sj));
+      p.i_begin = (int64_t)b;
+      p.n = (int64_t)e;
+      r = launch(ctx, p, cl::MODE_STEP, sj);
+      if (r) return r;
+    }
+    CU(cudaEventRecord(h.ev_join, h.side));
+    CU(cudaStreamWaitEvent(st, h.ev_join, 0));
+  } else {
+    if (stage_copy) memcpy(h.h_act, action_host, N * A * sizeof(float));
+    if (!host_in) CU(cudaMemcpyAsync(h.d_act, h.h_act, N * A * sizeof(float), cudaMemcpyHostToDevice, st));
+    r = launch(ctx, p, cl::MODE_STEP, st);
+    if (r) return r;
+  }
   ctx->step_index += 1;
-  if (!zc) CU(cudaMemcpyAsync(s.out, h.d_out, h.out_bytes, cudaMemcpyDeviceToHost, st));
+  if (!host_out) CU(cudaMemcpyAsync(s.out, h.d_out, h.out_bytes, cudaMemcpyDeviceToHost, st));
   h.pending = true;
   return CL_OK;
 }
 
 extern "C" int cl_host_set_zero_copy(cl_ctx* ctx, int enable) {
+  return cl_host_set_mode(ctx, enable ? CL_HOST_ZEROCOPY : CL_HOST_DMA, 1);
+}
+
+extern "C" int cl_host_set_mode(cl_ctx* ctx, int mode, int slices) {
   if (!ctx) return CL_EINVAL;
+  if (mode < CL_HOST_DMA || mode > CL_HOST_PIPELINED || slices < 1 || slices > 64)
+    return fail(ctx, CL_EINVAL, "cl_host_set_mode: mode %d / slices %d out of range", mode, slices);
   int r = host_stage_init(ctx);
   if (r) return r;
-  ctx->hs.zero_copy = enable != 0;
+  if (ctx->hs.pending) return fail(ctx, CL_EINVAL, "cl_host_set_mode with a step in flight");
+  ctx->hs.mode = mode;
+  ctx->hs.slices = slices;
   return CL_OK;
 }
 
@@ -540,7 +600,7 @@ static int host_wait_common(cl_ctx* ctx, void* stream, int64_t* n_done_out) {
   HostSlot& s = h.slot[h.cur];
   int64_t nd = 0;
   for (size_t i = 0; i < N; ++i) nd += (s.done[i] != 0);
-  if (nd > 0) {  // rare: fetch the terminal observations and Monitor numbers
+  if (nd > 0 && !h.extras_on_host) {  // DMA mode: fetch the terminal observations and Monitor numbers
     CU(cudaMemcpyAsync(s.term_obs, h.d_term, N * O * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(s.last_ep_ret, h.d_ler, N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(s.last_ep_len, h.d_lel, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

@@ -17,6 +17,7 @@ namespace cl {
 
 struct KParams {
   int64_t n, n_pad, env_id_base;
+  int64_t i_begin;        // first env of this launch (host path: env slices pipelined over streams)
   uint32_t k0, k1;
   uint64_t step_index;
   // graph mode: the Philox step index lives on the device so that CUDA-graph replays advance it
@@ -217,7 +218,8 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
                                         // otherwise cost an atomic every step)
 
   // warp-aggregated statistics (one set of atomics per warp, only when something ended)
-  const unsigned dm = __ballot_sync(0xffffffffu, live && done && autoreset);
+  const unsigned dall = __ballot_sync(0xffffffffu, live && done);
+  const unsigned dm = autoreset ? dall : 0u;
   const unsigned bm = __ballot_sync(0xffffffffu, live && bad);
   if (dm) {
     const bool mine = (dm >> lane) & 1u;
@@ -239,8 +241,15 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
                           // serialise every warp on one atomic each interval)
 
   const int64_t oo = ROLL ? t * p.obs_ts : 0;
+  const bool rows_fast = p.rows_fast != 0;  // warp-uniform
+  if (dall && rows_fast && p.term_obs) {
+    // a warp with a finished episode writes all 32 of its rows (whole 128-byte lines; the host
+    // path points term_obs at pinned host memory, where scattered 4-byte stores would each be
+    // a PCIe transaction).  Rows of unfinished envs are not meaningful and never read.
+    store_obs_rows_warp<real, E::OBS>(sm_rows, (float*)p.term_obs + oo, i - (int64_t)lane, p.n, lane, obs);
+  }
   if (live && done) {
-    if (p.term_obs) store_obs<real>(p.term_obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
+    if (p.term_obs && !rows_fast) store_obs<real>(p.term_obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
     if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;
     if (p.last_ep_len) p.last_ep_len[i] = ep_len;
     if (autoreset) {
@@ -251,7 +260,6 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
     }
   }
   // warp-uniform: contiguous float32 rows -> coalesced vector stores through shared memory
-  const bool rows_fast = p.rows_fast != 0;
   if (rows_fast)
     store_obs_rows_warp<real, E::OBS>(sm_rows, (float*)p.obs + oo, i - (int64_t)lane, p.n, lane, obs);
   if (live) {
@@ -281,7 +289,7 @@ __device__ __forceinline__ void synth_action(const KParams& p, const Stream& rng
 template <class E, bool ROLL>
 __global__ void __launch_bounds__(256) k_step(const KParams p) {
   extern __shared__ __align__(16) float sm_rows_all[];  // [warps per block][32 * OBS], row-store staging
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = p.i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < p.n;
   const unsigned lane = threadIdx.x & 31u;
   float* sm_rows = sm_rows_all + (threadIdx.x >> 5) * (32 * E::OBS);
@@ -538,7 +546,8 @@ __global__ void __launch_bounds__(256) k_init(const KParams p) {
 template <class E>
 inline bool rows_fast_ok(const KParams& p, bool rollout) {
   return p.obs != nullptr && !(p.flags & CL_F_OBS_F64) && p.obs_cs == 1 && p.obs_es == E::OBS &&
-         ((uintptr_t)p.obs % 16) == 0 && (!rollout || (p.obs_ts % 4) == 0);
+         ((uintptr_t)p.obs % 16) == 0 && (!rollout || (p.obs_ts % 4) == 0) &&
+         ((uintptr_t)p.term_obs % 16) == 0;  // term_obs (if any) shares the obs layout
 }
 
 template <class E>
@@ -547,7 +556,7 @@ cudaError_t launch_env(const KParams& p_in, int mode, cudaStream_t st, int block
   const bool roll = (mode == MODE_ROLLOUT || mode == MODE_ROLLOUT_DYN);
   p.rows_fast = (mode == MODE_STEP || roll) && rows_fast_ok<E>(p, roll) ? 1 : 0;
   const size_t row_smem = p.rows_fast ? (size_t)(block / 32) * 32 * E::OBS * sizeof(float) : 0;
-  const unsigned grid = (unsigned)((p.n + block - 1) / block);
+  const unsigned grid = (unsigned)((p.n - p.i_begin + block - 1) / block);  // i_begin != 0 only for MODE_STEP
   switch (mode) {
     // dynamic smem only when observations go out as contiguous float32 rows (row-store staging)
     case MODE_STEP: k_step<E, false><<<grid, block, row_smem, st>>>(p); break;

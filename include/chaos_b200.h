@@ -241,6 +241,16 @@ int cl_host_action_staging(cl_ctx* ctx, float** action_pinned);
 /* zero-copy variant of the host path: the step kernel reads actions from / writes results to the
  * pinned (UVA-mapped) host buffers directly instead of DMA copies around it */
 int cl_host_set_zero_copy(cl_ctx* ctx, int enable);
+/* how cl_step_host_async moves the data (default: PIPELINED with 2-4 slices from 16,384 envs up,
+ * ZEROCOPY below):
+ *   CL_HOST_DMA        H2D copy of the actions -> step kernel -> one D2H copy of obs|reward|done
+ *   CL_HOST_ZEROCOPY   one launch; the kernel reads / writes the pinned host buffers itself
+ *   CL_HOST_PIPELINED  `slices` env slices alternate over two streams: per slice a DMA copy of its
+ *                      actions, then its step kernel writing the results to pinned host memory, so
+ *                      upstream and downstream PCIe traffic of neighbouring slices overlap.
+ * Results are identical in all three modes (same kernel, same per-env Philox streams). */
+enum { CL_HOST_DMA = 0, CL_HOST_ZEROCOPY = 1, CL_HOST_PIPELINED = 2 };
+int cl_host_set_mode(cl_ctx* ctx, int mode, int slices);
 int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* buf, const float* action_host);
 int cl_step_host_wait(cl_ctx* ctx, void* stream, float* obs_host, float* reward_host,
                       uint8_t* done_host, float* term_obs_host, double* last_ep_ret_host,

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Host-buffer VecEnv step time vs data-movement mode (cl_host_set_mode): us per step."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import numpy as np, torch
+from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+
+kind = sys.argv[1] if len(sys.argv) > 1 else "lorenz_rk4"
+sizes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [4096, 16384, 65536, 262144]
+modes = [("dma", 1), ("zerocopy", 1), ("pipelined", 2), ("pipelined", 3), ("pipelined", 4), ("pipelined", 6),
+         ("pipelined", 8), ("pipelined", 16)]
+for N in sizes:
+    env = BatchedChaosVecEnv(kind, N)
+    env.reset()
+    b = env.batch
+    rng = np.random.default_rng(0)
+    acts = [rng.uniform(-1, 1, (N, b.act_dim)).astype(np.float32) for _ in range(4)]
+    pin = b.host_action_buffer(); pin[:] = acts[0]
+
+    def bench(fn, n=400):
+        for _ in range(30): fn(0)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for k in range(n): fn(k)
+        torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e6
+
+    def pinned(k):
+        b.step_host_async(None); b.step_host_wait()
+    for mode, s in modes:
+        b.set_host_mode(mode, s)
+        row = {"kind": kind, "envs": N, "mode": mode, "slices": s,
+               "us_pinned_actions": round(bench(pinned), 2),
+               "us_ndarray_actions": round(bench(lambda k: env.step(acts[k % 4])), 2)}
+        print(json.dumps(row), flush=True)
+    env.close()
