@@ -136,6 +136,11 @@ class ChaosBatch:
         return self.lib.cl_dyn_launch_count(self.ctx)
 
     @property
+    def plain_launch_count(self) -> int:
+        """Rollouts that ran on the plain-I/O kernel instantiation (FP64-bound kinds)."""
+        return self.lib.cl_plain_launch_count(self.ctx)
+
+    @property
     def launch_count(self) -> int:
         return self.lib.cl_launch_count(self.ctx)
 

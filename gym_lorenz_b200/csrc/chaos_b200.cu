@@ -90,7 +90,9 @@ struct cl_ctx {
   uint64_t* d_step;     // graph mode: device-resident Philox step index (+ ticket word behind it)
   int graph_mode;
   int dyn_bps;          // resident worker blocks per SM (0 = not yet queried)
+  int no_plain;         // never pick the plain-rollout kernel instantiation
   int64_t dyn_launches;
+  int64_t plain_launches;  // rollouts that ran on the plain-I/O kernel instantiation
 };
 
 static char g_err[512] = "";
@@ -169,6 +171,8 @@ extern "C" int cl_create(const cl_config* cfg, cl_ctx** out) {
     const int b = atoi(ov);
     if (b >= 32 && b <= 256 && (b % 32) == 0) ctx->block = b;
   }
+  // testing / A-B override: CHAOS_B200_PLAIN=0 keeps rollouts on the generic kernel instantiation
+  ctx->no_plain = (getenv("CHAOS_B200_PLAIN") != nullptr && getenv("CHAOS_B200_PLAIN")[0] == '0') ? 1 : 0;
   ctx->step_index = 0;
   e = cudaSetDevice(cfg->device);
   if (e != cudaSuccess) { int r = fail(nullptr, CL_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); free(ctx); return r; }
@@ -242,6 +246,7 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
   p.n = c.num_envs; p.n_pad = c.n_pad; p.env_id_base = c.env_id_base;
   p.k0 = (uint32_t)c.seed; p.k1 = (uint32_t)(c.seed >> 32);
   p.step_index = ctx->step_index;
+  p.no_plain = ctx->no_plain;
   if (ctx->graph_mode) p.step_ptr = ctx->d_step;
   p.max_steps = c.max_episode_steps; p.substeps = c.substeps; p.flags = c.flags;
   p.dt = c.dt; p.alpha = c.alpha; p.act_limit = c.act_limit; p.act_gain = c.act_gain;
@@ -270,11 +275,15 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
 
 __global__ void k_advance_step(uint64_t* step, uint64_t count) { *step += count; }
 
-static int launch(cl_ctx* ctx, const KParams& p, int mode, cudaStream_t st) {
+static int launch(cl_ctx* ctx, const KParams& p_in, int mode, cudaStream_t st) {
+  KParams p = p_in;
+  int32_t plain = 0;
+  p.host_plain_out = &plain;
   cudaError_t e = is_parity(ctx->cfg.kind) ? cl_launch_parity(ctx->cfg.kind, p, mode, st, ctx->block)
                                            : cl_launch_northstar(ctx->cfg.kind, p, mode, st, ctx->block);
   if (e != cudaSuccess) return fail(ctx, CL_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   ctx->launches += 1;
+  ctx->plain_launches += plain;
   if (ctx->graph_mode && mode != cl::MODE_INIT) {  // device-resident Philox step index (CUDA graphs)
     const uint64_t count = (mode == cl::MODE_ROLLOUT || mode == cl::MODE_ROLLOUT_DYN) ? (uint64_t)p.T : 1;
     k_advance_step<<<1, 1, 0, st>>>(ctx->d_step, count);
@@ -386,6 +395,7 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
 }
 
 extern "C" int64_t cl_dyn_launch_count(const cl_ctx* ctx) { return ctx ? ctx->dyn_launches : 0; }
+extern "C" int64_t cl_plain_launch_count(const cl_ctx* ctx) { return ctx ? ctx->plain_launches : 0; }
 
 extern "C" int cl_derivatives(cl_ctx* ctx, void* stream, const void* state, const float* action,
                               void* out, int64_t n) {

@@ -65,6 +65,8 @@ struct KParams {
   int32_t dyn_chunk, dyn_nchunks, dyn_nwarps, dyn_tma, dyn_grid;
   // observations go out as contiguous, 16-byte aligned float32 rows -> warp-transposed vector stores
   int32_t rows_fast;
+  int32_t no_plain;  // host-side only: keep the generic instantiation (tests, A/B runs)
+  int32_t* host_plain_out;  // host-side only: launch_env reports which instantiation it launched
 };
 
 enum LaunchMode { MODE_STEP = 0, MODE_ROLLOUT = 1, MODE_RESET = 2, MODE_INIT = 3, MODE_ROLLOUT_DYN = 4 };
@@ -188,10 +190,34 @@ __device__ __forceinline__ void store_obs_rows_warp(float* __restrict__ sm, floa
 
 // ---- one control interval of one env (shared by the static and the dynamic kernels) ----
 
-template <class E, bool ROLL>
+// The "plain rollout" I/O shape -- what a synthetic-action benchmark or a device-side collector
+// uses: canonical time-major float32 observation planes [T][OBS][n_pad], reward [T][n_pad] in the env's real type, done
+// flags, auto-reset on, no terminal-observation buffer, actions given (staged by
+// bulk copies in the dynamic kernel).  For the kinds whose rollout is FP64-pipe bound
+// (PlainRollout<E>::value) the rollout kernels are instantiated a second time with these as
+// compile-time facts: the generic interval executes ~245 non-FP64 instructions per warp (runtime
+// layout / null-pointer tests, 64-bit stride arithmetic), the plain one under half of that, and
+// with only ~3 warps per scheduler every epilogue instruction shows (-5 % launch time at 65,536 envs).
+// launch_env() picks the instantiation from the launch parameters; results are identical.
+template <class E> struct PlainRollout { enum { value = 0 }; };
+template <int N> struct SpecTag { enum { value = N }; };
+
+// SPEC: warp-uniform specialisation of E::step chosen once per launch / task (0 = generic).  Kinds
+// with PlainRollout<E>::value provide `static int spec(const S&, const KParams&)` (evaluated by all
+// 32 lanes) and `template <int SPEC> step_spec(...)`; the plain rollout kernels then run one of two
+// separately compiled interval loops, each a straight line of code (e.g. Lorenz: nominal parameters
+// as constant-bank operands + 16 unrolled substeps) instead of branching per interval.
+template <class E, int SPEC>
+__device__ __forceinline__ void step_dispatch(typename E::S& s, const KParams& p, const float* a, const double* nz,
+                                              typename E::real* obs, typename E::real& rew, bool& term) {
+  if constexpr (SPEC != 0) E::template step_spec<SPEC>(s, p, a, nz, obs, rew, term);
+  else E::step(s, p, a, nz, obs, rew, term);
+}
+
+template <class E, bool ROLL, bool PLAIN = false, int SPEC = 0>
 __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, double& ep_ret,
                                              const KParams& p, const int64_t i, const bool live,
-                                             const unsigned lane, const int t, const Stream& rng,
+                                             const unsigned lane, const int t, const uint64_t step,
                                              const float* a, const bool want_noise, const bool obs64,
                                              const bool autoreset, unsigned& bad_acc, float* sm_rows, bool& fin) {
   typedef typename E::real real;
@@ -202,7 +228,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
 #pragma unroll
       for (int c = 0; c < E::NOISE; ++c) nz[c] = live ? p.noise[c * p.n_pad + i] : 0.0;
     } else {
-      draw_normal<(E::NOISE > 0 ? E::NOISE : 1)>(rng, TAG_NOISE, nz);
+      draw_normal<(E::NOISE > 0 ? E::NOISE : 1)>(make_stream(p, i, step), TAG_NOISE, nz);
     }
   }
 
@@ -210,7 +236,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
   real rew;
   bool term;
   const bool was_finite = fin;  // finiteness is carried from the previous interval, not recomputed
-  E::step(s, p, a, nz, obs, rew, term);
+  step_dispatch<E, SPEC>(s, p, a, nz, obs, rew, term);
   ep_len += 1;
   ep_ret += (double)rew;
   const bool trunc = E::time_limit(p, ep_len);
@@ -220,7 +246,8 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
                                         // otherwise cost an atomic every step)
 
   // warp-aggregated statistics (one set of atomics per warp, only when something ended)
-  const unsigned dall = __ballot_sync(0xffffffffu, live && done);
+  const bool has_term = !PLAIN && p.term_obs != nullptr;
+  const unsigned dall = __ballot_sync(0xffffffffu, live && done && (autoreset || has_term));
   const unsigned dm = autoreset ? dall : 0u;
   const unsigned bm = __ballot_sync(0xffffffffu, live && bad);
   if (dm) {
@@ -243,19 +270,19 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
                           // serialise every warp on one atomic each interval)
 
   const int64_t oo = ROLL ? t * p.obs_ts : 0;
-  const bool rows_fast = p.rows_fast != 0;  // warp-uniform
-  if (dall && rows_fast && p.term_obs) {
+  const bool rows_fast = !PLAIN && p.rows_fast != 0;  // warp-uniform
+  if (has_term && rows_fast && dall) {
     // a warp with a finished episode writes all 32 of its rows (whole 128-byte lines; the host
     // path points term_obs at pinned host memory, where scattered 4-byte stores would each be
     // a PCIe transaction).  Rows of unfinished envs are not meaningful and never read.
     store_obs_rows_warp<real, E::OBS>(sm_rows, (float*)p.term_obs + oo, i - (int64_t)lane, p.n, lane, obs);
   }
   if (live && done) {
-    if (p.term_obs && !rows_fast) store_obs<real>(p.term_obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
-    if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;
+    if (has_term && !rows_fast) store_obs<real>(p.term_obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
+    if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;   // tested only when an episode ends
     if (p.last_ep_len) p.last_ep_len[i] = ep_len;
     if (autoreset) {
-      E::reset(s, p, rng, obs);
+      E::reset(s, p, make_stream(p, i, step), obs);  // the Philox stream is only built when it is needed
       ep_len = 0;
       ep_ret = 0.0;
       fin = true;
@@ -265,15 +292,24 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
   if (rows_fast)
     store_obs_rows_warp<real, E::OBS>(sm_rows, (float*)p.obs + oo, i - (int64_t)lane, p.n, lane, obs);
   if (live) {
-    if (p.obs && !rows_fast) store_obs<real>(p.obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
-    if (p.reward) {
-      const int64_t ro = (ROLL ? t * p.rew_ts : 0) + i;
-      if (p.reward_f32) ((float*)p.reward)[ro] = (float)rew;
-      else ((real*)p.reward)[ro] = rew;
-    }
-    if (p.done) {
-      p.done[(ROLL ? t * p.done_ts : 0) + i] =
-          (uint8_t)((term ? CL_DONE_TERMINATED : 0) | (trunc ? CL_DONE_TRUNCATED : 0));
+    const uint8_t dflags = (uint8_t)((term ? CL_DONE_TERMINATED : 0) | (trunc ? CL_DONE_TRUNCATED : 0));
+    if (PLAIN) {
+      // canonical time-major planes obs[T][OBS][n_pad], reward[T][n_pad], done[T][n_pad]: every
+      // stride derives from n_pad (uniform registers are scarce in this loop, see PlainRollout)
+      const int64_t np = p.n_pad, row = (int64_t)t * np + i;
+      float* o = (float*)p.obs + (int64_t)t * (E::OBS * np) + i;
+#pragma unroll
+      for (int c = 0; c < E::OBS; ++c) o[c * np] = (float)obs[c];
+      ((real*)p.reward)[row] = rew;
+      p.done[row] = dflags;
+    } else {
+      if (p.obs && !rows_fast) store_obs<real>(p.obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
+      if (p.reward) {
+        const int64_t ro = (ROLL ? t * p.rew_ts : 0) + i;
+        if (p.reward_f32) ((float*)p.reward)[ro] = (float)rew;
+        else ((real*)p.reward)[ro] = rew;
+      }
+      if (p.done) p.done[(ROLL ? t * p.done_ts : 0) + i] = dflags;
     }
   }
 }
@@ -288,7 +324,7 @@ __device__ __forceinline__ void synth_action(const KParams& p, const Stream& rng
 
 // ---- the static step / rollout kernel: thread i owns env i for the whole launch ----------
 
-template <class E, bool ROLL>
+template <class E, bool ROLL, bool PLAIN = false>
 __global__ void __launch_bounds__(256) k_step(const KParams p) {
   extern __shared__ __align__(16) float sm_rows_all[];  // [warps per block][32 * OBS], row-store staging
   const int64_t i = p.i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,9 +341,9 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
     ep_ret = p.ep_return[i];
   }
   E::prepare(s, p, live);  // executed by all 32 lanes (may vote)
-  const bool obs64 = (p.flags & CL_F_OBS_F64) != 0;
-  const bool autoreset = (p.flags & CL_F_AUTORESET) != 0;
-  const bool want_noise = E::NOISE > 0 && E::uses_noise(p);
+  const bool obs64 = !PLAIN && (p.flags & CL_F_OBS_F64) != 0;
+  const bool autoreset = PLAIN || (p.flags & CL_F_AUTORESET) != 0;
+  const bool want_noise = !PLAIN && E::NOISE > 0 && E::uses_noise(p);
   const int T = ROLL ? p.T : 1;
 
   // actions are fetched one control interval ahead; this only hides their latency while
@@ -316,26 +352,35 @@ __global__ void __launch_bounds__(256) k_step(const KParams p) {
   float a_next[E::ACT];
 #pragma unroll
   for (int c = 0; c < E::ACT; ++c)
-    a_next[c] = (live && p.action != nullptr) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
+    a_next[c] = (live && (PLAIN || p.action != nullptr)) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
 
   unsigned bad_acc = 0u;
   bool fin = E::finite(s);
   const uint64_t step0 = step_base(p);
-  for (int t = 0; t < T; ++t) {
-    const Stream rng = make_stream(p, i, step0 + (uint64_t)t);
-    float a[E::ACT];
-    if (ROLL && p.action == nullptr) {
-      synth_action<E>(p, rng, a);
-    } else {
+  auto intervals = [&](auto spec_tag) {
+    constexpr int SPEC = decltype(spec_tag)::value;
+    for (int t = 0; t < T; ++t) {
+      const uint64_t step = step0 + (uint64_t)t;
+      float a[E::ACT];
+      if (ROLL && !PLAIN && p.action == nullptr) {
+        synth_action<E>(p, make_stream(p, i, step), a);
+      } else {
 #pragma unroll
-      for (int c = 0; c < E::ACT; ++c) a[c] = a_next[c];
-      if (ROLL && live && t + 1 < T) {
+        for (int c = 0; c < E::ACT; ++c) a[c] = a_next[c];
+        if (ROLL && live && t + 1 < T) {
 #pragma unroll
-        for (int c = 0; c < E::ACT; ++c)
-          a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
+          for (int c = 0; c < E::ACT; ++c)
+            a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
+        }
       }
+      env_interval<E, ROLL, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin);
     }
-    env_interval<E, ROLL>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin);
+  };
+  if constexpr (PLAIN) {
+    if (E::spec(s, p) == 1) intervals(SpecTag<1>{});
+    else intervals(SpecTag<0>{});
+  } else {
+    intervals(SpecTag<0>{});
   }
   if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
   if (live) {
@@ -394,7 +439,7 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <class E>
+template <class E, bool PLAIN = false>
 __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ __align__(16) float sm_rows_all[4][32 * E::OBS];
@@ -406,7 +451,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
   const int per_buf = Tc * E::ACT * 32;  // floats
   float* abuf = (float*)dyn_smem + (size_t)wib * per_buf;
   uint64_t* mbar = (uint64_t*)(dyn_smem + (size_t)wpb * per_buf * sizeof(float)) + wib;
-  const bool tma = p.dyn_tma != 0;
+  const bool tma = PLAIN || p.dyn_tma != 0;
   if (tma) {
     if (lane == 0) {
       mbar_init(&mbar[0], 1);
@@ -414,9 +459,9 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     }
     __syncwarp();
   }
-  const bool obs64 = (p.flags & CL_F_OBS_F64) != 0;
-  const bool autoreset = (p.flags & CL_F_AUTORESET) != 0;
-  const bool want_noise = E::NOISE > 0 && E::uses_noise(p);
+  const bool obs64 = !PLAIN && (p.flags & CL_F_OBS_F64) != 0;
+  const bool autoreset = PLAIN || (p.flags & CL_F_AUTORESET) != 0;
+  const bool want_noise = !PLAIN && E::NOISE > 0 && E::uses_noise(p);
   const uint32_t W = (uint32_t)p.dyn_nwarps, total = W * (uint32_t)p.dyn_nchunks;
 
   auto grab = [&]() -> uint32_t {
@@ -483,21 +528,30 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     const float* ab = abuf;
     unsigned bad_acc = 0u;
     bool fin = E::finite(s);
-    for (int tl = 0; tl < len; ++tl) {
-      const int t = t0 + tl;
-      const Stream rng = make_stream(p, i, step0 + (uint64_t)t);
-      float a[E::ACT];
-      if (p.action == nullptr) {
-        synth_action<E>(p, rng, a);
-      } else if (tma) {
+    auto intervals = [&](auto spec_tag) {
+      constexpr int SPEC = decltype(spec_tag)::value;
+      for (int tl = 0; tl < len; ++tl) {
+        const int t = t0 + tl;
+        const uint64_t step = step0 + (uint64_t)t;
+        float a[E::ACT];
+        if (!PLAIN && p.action == nullptr) {
+          synth_action<E>(p, make_stream(p, i, step), a);
+        } else if (tma) {
 #pragma unroll
-        for (int cc = 0; cc < E::ACT; ++cc) a[cc] = ab[(tl * E::ACT + cc) * 32 + lane];
-      } else {
+          for (int cc = 0; cc < E::ACT; ++cc) a[cc] = ab[(tl * E::ACT + cc) * 32 + lane];
+        } else {
 #pragma unroll
-        for (int cc = 0; cc < E::ACT; ++cc)
-          a[cc] = live ? p.action[(int64_t)t * p.act_ts + i * p.act_es + cc * p.act_cs] : 0.0f;
+          for (int cc = 0; cc < E::ACT; ++cc)
+            a[cc] = live ? p.action[(int64_t)t * p.act_ts + i * p.act_es + cc * p.act_cs] : 0.0f;
+        }
+        env_interval<E, true, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin);
       }
-      env_interval<E, true>(s, ep_len, ep_ret, p, i, live, lane, t, rng, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin);
+    };
+    if constexpr (PLAIN) {
+      if (E::spec(s, p) == 1) intervals(SpecTag<1>{});
+      else intervals(SpecTag<0>{});
+    } else {
+      intervals(SpecTag<0>{});
     }
     if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
     bad_acc = 0u;
@@ -552,23 +606,41 @@ inline bool rows_fast_ok(const KParams& p, bool rollout) {
          ((uintptr_t)p.term_obs % 16) == 0;  // term_obs (if any) shares the obs layout
 }
 
+// Plain-rollout instantiation (see PlainRollout): decided once per launch on the host.
+template <class E>
+inline bool plain_rollout_ok(const KParams& p, int mode) {
+  return PlainRollout<E>::value && !p.no_plain && E::NOISE == 0 && p.action != nullptr && p.obs != nullptr && p.obs_es == 1 &&
+         p.obs_cs == p.n_pad && p.obs_ts == (int64_t)E::OBS * p.n_pad && p.rew_ts == p.n_pad && p.done_ts == p.n_pad &&
+         !(p.flags & CL_F_OBS_F64) && !p.rows_fast && p.reward != nullptr && !p.reward_f32 && p.done != nullptr &&
+         p.term_obs == nullptr &&
+         (p.flags & CL_F_AUTORESET) && (mode != MODE_ROLLOUT_DYN || p.dyn_tma);
+}
+
 template <class E>
 cudaError_t launch_env(const KParams& p_in, int mode, cudaStream_t st, int block) {
   KParams p = p_in;
   const bool roll = (mode == MODE_ROLLOUT || mode == MODE_ROLLOUT_DYN);
   p.rows_fast = (mode == MODE_STEP || roll) && rows_fast_ok<E>(p, roll) ? 1 : 0;
+  constexpr bool HAS_PLAIN = PlainRollout<E>::value != 0;
+  const bool plain = roll && plain_rollout_ok<E>(p, mode);
+  if (p.host_plain_out) *p.host_plain_out = plain ? 1 : 0;
+  p.host_plain_out = nullptr;
   const size_t row_smem = p.rows_fast ? (size_t)(block / 32) * 32 * E::OBS * sizeof(float) : 0;
   const unsigned grid = (unsigned)((p.n - p.i_begin + block - 1) / block);  // i_begin != 0 only for MODE_STEP
   switch (mode) {
     // dynamic smem only when observations go out as contiguous float32 rows (row-store staging)
     case MODE_STEP: k_step<E, false><<<grid, block, row_smem, st>>>(p); break;
-    case MODE_ROLLOUT: k_step<E, true><<<grid, block, row_smem, st>>>(p); break;
+    case MODE_ROLLOUT:
+      if (plain) k_step<E, true, HAS_PLAIN><<<grid, block, row_smem, st>>>(p);
+      else k_step<E, true><<<grid, block, row_smem, st>>>(p);
+      break;
     case MODE_RESET: k_reset<E><<<grid, block, 0, st>>>(p); break;
     case MODE_INIT: k_init<E><<<grid, block, 0, st>>>(p); break;
     case MODE_ROLLOUT_DYN: {
       // block = 128 threads (one warp per scheduler), p.dyn_grid blocks, smem = action staging
       const size_t smem = (size_t)4 * p.dyn_chunk * E::ACT * 32 * sizeof(float) + 4 * sizeof(uint64_t);
-      k_rollout_dyn<E><<<(unsigned)p.dyn_grid, 128, smem, st>>>(p);
+      if (plain) k_rollout_dyn<E, HAS_PLAIN><<<(unsigned)p.dyn_grid, 128, smem, st>>>(p);
+      else k_rollout_dyn<E><<<(unsigned)p.dyn_grid, 128, smem, st>>>(p);
       break;
     }
     default: return cudaErrorInvalidValue;
@@ -581,7 +653,17 @@ cudaError_t dyn_occupancy(int chunk, int* blocks_per_sm) {
   const size_t smem = (size_t)4 * chunk * E::ACT * 32 * sizeof(float) + 4 * sizeof(uint64_t);
   cudaError_t e = cudaFuncSetAttribute(k_rollout_dyn<E>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_rollout_dyn<E>, 128, smem);
+  int occ = 0, occ_plain = 1 << 30;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rollout_dyn<E>, 128, smem);
+  if (e != cudaSuccess) return e;
+  if (PlainRollout<E>::value) {  // the worker grid must be resident whichever instantiation is launched
+    e = cudaFuncSetAttribute(k_rollout_dyn<E, PlainRollout<E>::value != 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_plain, k_rollout_dyn<E, PlainRollout<E>::value != 0>, 128, smem);
+    if (e != cudaSuccess) return e;
+  }
+  *blocks_per_sm = occ < occ_plain ? occ : occ_plain;
+  return cudaSuccess;
 }
 
 // plane accessors

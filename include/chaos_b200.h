@@ -271,6 +271,9 @@ int64_t cl_launch_count(const cl_ctx* ctx);
 int cl_block_size(const cl_ctx* ctx);
 /* cl_rollout calls served by the dynamically scheduled kernel (env-warp x interval-chunk tasks) */
 int64_t cl_dyn_launch_count(const cl_ctx* ctx);
+/* rollouts that ran on the plain-I/O instantiation of the rollout kernels (FP64-bound kinds:
+ * float32 SoA observation planes, real-typed reward, done flags, auto-reset, no term_obs) */
+int64_t cl_plain_launch_count(const cl_ctx* ctx);
 
 /* -- device-side SB3 plumbing that directly follows the env step; all
  *    pointers are DEVICE pointers, calls only enqueue on `stream` of the current device. */

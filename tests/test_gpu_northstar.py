@@ -261,3 +261,33 @@ def test_row_major_observation_rollout_equals_plane_layout(kind, n, monkeypatch)
         planes, rows = outs
         assert rows.shape == (T, n, planes.shape[1])
         assert torch.equal(torch.nan_to_num(planes[:, :, :n].permute(0, 2, 1)), torch.nan_to_num(rows))
+
+
+@pytest.mark.parametrize("kind,n,T", [("lorenz_rk4", 65536 + 40, 40), ("pmsm_rk4", 9000, 19), ("lorenz_rk4", 3000, 21)])
+def test_plain_rollout_instantiation_equals_generic_bitwise(kind, n, T, monkeypatch):
+    """The rollout kernels exist twice for the FP64-bound kinds: generic, and with the plain I/O
+    shape as compile-time facts (kernels_common.cuh PlainRollout).  Same inputs -> same bits, on
+    the dynamic (65,576 envs: env-warps do not divide over the schedulers) and the static kernel,
+    with episodes ending inside the window."""
+    import torch
+    outs = []
+    for plain in ("1", "0"):
+        monkeypatch.setenv("CHAOS_B200_PLAIN", plain)
+        b = H.gpu_batch(kind, n, seed=9, autoreset=True, max_episode_steps=6, substeps=16 if kind == "lorenz_rk4" else 3)
+        b.reset()
+        g = torch.Generator(device="cpu").manual_seed(1)
+        acts = (torch.rand((T, b.act_dim, b.n_pad), generator=g) * 2 - 1).to(b.device)
+        acts[:, :, 5] = 0.0
+        o = b.rollout(T, acts[:, :, :n].permute(0, 2, 1))
+        outs.append((o["obs"].clone(), o["reward"].clone(), o["done"].clone(), b.state.clone(), b.ep_len.clone(),
+                     b.ep_return.clone(), dict(b.stats()), b.dyn_launch_count))
+        assert b.plain_launch_count == (1 if plain == "1" else 0)
+        b.close()
+    a, c = outs
+    assert a[7] == c[7] and (a[7] > 0) == (n > 65536)
+    for k in range(6):
+        assert torch.equal(a[k][..., :n], c[k][..., :n]), k
+    for key in ("episodes", "length_sum", "terminated", "truncated", "nonfinite_events"):
+        assert a[6][key] == c[6][key], key
+    assert a[6]["episodes"] > 0
+    assert np.isclose(a[6]["return_sum"], c[6]["return_sum"], rtol=1e-12)   # atomics: order differs
