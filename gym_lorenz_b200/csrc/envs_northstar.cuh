@@ -128,19 +128,24 @@ struct EnvLorenzRK4 {
   // SPEC 1: every env of the warp carries the nominal parameters AND S == 16 (the benchmark
   // configuration): constant-bank parameters, 16 unrolled substeps, no per-interval dispatch.
   __device__ static int spec(const S& s, const KParams& p) {
-    return (sizeof(R) == 8 && s.uni && p.substeps == 16) ? 1 : 0;
+    return (s.uni && p.substeps == 16) ? 1 : 0;
   }
   template <int SPEC>
   __device__ static void step_spec(S& s, const KParams& p, const float* a, const double*, R* obs, R& rew,
                                    bool& term) {
     static_assert(SPEC == 1, "unknown specialisation");
     const float lim = p.act_limit_f;
-    const R g = (R)p.act_gain;
+    const R g = sizeof(R) == 8 ? (R)p.act_gain : (R)p.act_gain_f;
     const R u1 = mul_keep((R)clipf(a[0], -lim, lim), g);
     const R u2 = mul_keep((R)clipf(a[1], -lim, lim), g);
     const R u3 = mul_keep((R)clipf(a[2], -lim, lim), g);
-    const LorenzPar<R> qc = {(R)p.nom[0], (R)p.nom[1], (R)p.nom[2]};
-    lorenz_rk4_fixed<R, 16>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6);
+    if (sizeof(R) == 8) {
+      const LorenzPar<R> qc = {(R)p.nom[0], (R)p.nom[1], (R)p.nom[2]};
+      lorenz_rk4_fixed<R, 16>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6);
+    } else {
+      const LorenzPar<R> qc = {(R)p.nomf[0], (R)p.nomf[1], (R)p.nomf[2]};
+      lorenz_rk4_fixed<R, 16>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f);
+    }
     // with the env's own (register) parameters: f(s) + 0 with CONSTANT parameters would need two
     // non-register operands in one DFMA, which forces the constants into registers -- and ptxas
     // then keeps using those registers inside the integrator (3-register DFMAs again)
@@ -298,6 +303,7 @@ struct EnvPMSMRK4 {
 };
 
 template <> struct PlainRollout<EnvLorenzRK4<double>> { enum { value = 1 }; };
+template <> struct PlainRollout<EnvLorenzRK4<float>> { enum { value = 1 }; };   // issue-slot bound: same remedy
 template <> struct PlainRollout<EnvPMSMRK4> { enum { value = 1 }; };
 
 }  // namespace cl

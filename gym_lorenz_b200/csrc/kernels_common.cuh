@@ -193,7 +193,7 @@ __device__ __forceinline__ void store_obs_rows_warp(float* __restrict__ sm, floa
 // The "plain rollout" I/O shape -- what a synthetic-action benchmark or a device-side collector
 // uses: canonical time-major float32 observation planes [T][OBS][n_pad], reward [T][n_pad] in the env's real type, done
 // flags, auto-reset on, no terminal-observation buffer, actions given (staged by
-// bulk copies in the dynamic kernel).  For the kinds whose rollout is FP64-pipe bound
+// bulk copies in the dynamic kernel).  For the kinds whose rollout is arithmetic / issue bound
 // (PlainRollout<E>::value) the rollout kernels are instantiated a second time with these as
 // compile-time facts: the generic interval executes ~245 non-FP64 instructions per warp (runtime
 // layout / null-pointer tests, 64-bit stride arithmetic), the plain one under half of that, and

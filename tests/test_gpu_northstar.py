@@ -263,7 +263,8 @@ def test_row_major_observation_rollout_equals_plane_layout(kind, n, monkeypatch)
         assert torch.equal(torch.nan_to_num(planes[:, :, :n].permute(0, 2, 1)), torch.nan_to_num(rows))
 
 
-@pytest.mark.parametrize("kind,n,T", [("lorenz_rk4", 65536 + 40, 40), ("pmsm_rk4", 9000, 19), ("lorenz_rk4", 3000, 21)])
+@pytest.mark.parametrize("kind,n,T", [("lorenz_rk4", 65536 + 40, 40), ("pmsm_rk4", 9000, 19), ("lorenz_rk4", 3000, 21),
+                                      ("lorenz_rk4_f32", 65536 + 40, 24), ("lorenz_rk4_f32", 5000, 11)])
 def test_plain_rollout_instantiation_equals_generic_bitwise(kind, n, T, monkeypatch):
     """The rollout kernels exist twice for the FP64-bound kinds: generic, and with the plain I/O
     shape as compile-time facts (kernels_common.cuh PlainRollout).  Same inputs -> same bits, on
@@ -273,7 +274,7 @@ def test_plain_rollout_instantiation_equals_generic_bitwise(kind, n, T, monkeypa
     outs = []
     for plain in ("1", "0"):
         monkeypatch.setenv("CHAOS_B200_PLAIN", plain)
-        b = H.gpu_batch(kind, n, seed=9, autoreset=True, max_episode_steps=6, substeps=16 if kind == "lorenz_rk4" else 3)
+        b = H.gpu_batch(kind, n, seed=9, autoreset=True, max_episode_steps=6, substeps=3 if kind == "pmsm_rk4" else 16)
         b.reset()
         g = torch.Generator(device="cpu").manual_seed(1)
         acts = (torch.rand((T, b.act_dim, b.n_pad), generator=g) * 2 - 1).to(b.device)
