@@ -307,6 +307,7 @@ def run_b200(args):
         ach = flops / (kern_ms * 1e-3) * 1e-12
         gbs = float(N) * T * bytes_step / (kern_ms * 1e-3) * 1e-9
         dyn = batch.dyn_launch_count > 0
+        plain = ", PLAIN=true" if batch.plain_launch_count > 0 else ""   # which instantiation launch_env picked
         traffic = traffic_detail = None
         try:   # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -318,8 +319,8 @@ def run_b200(args):
         except Exception:  # noqa: BLE001
             pass
         roofline = {
-            "kernel": (f"cl::k_rollout_dyn<{ENV_TYPE[args.kind]}> (fused T-interval rollout, env-warp x chunk tasks)" if dyn
-                       else f"cl::k_step<{ENV_TYPE[args.kind]}, ROLL=true> (fused T-interval rollout)"),
+            "kernel": (f"cl::k_rollout_dyn<{ENV_TYPE[args.kind]}{plain}> (fused T-interval rollout, env-warp x chunk tasks)" if dyn
+                       else f"cl::k_step<{ENV_TYPE[args.kind]}, ROLL=true{plain}> (fused T-interval rollout)"),
             "bound": "fp64" if fma_bytes == 8 else "fp32", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": ach / fp64_peak if fp64_peak > 0 else None, "traffic": traffic, "traffic_detail": traffic_detail,
             "peak_source": "DFMA-chain micro-kernel (cl_measure_fma_peak) run in this process, 2 flop/FMA; "
