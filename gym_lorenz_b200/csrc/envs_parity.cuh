@@ -692,4 +692,14 @@ struct EnvPMSMFree {
   }
 };
 
+template <> struct StepMinBlocks<EnvLorenz3> { enum { value = 5 }; };
+template <> struct StepMinBlocks<EnvLorenz3Pair> { enum { value = 4 }; };
+template <> struct StepMinBlocks<EnvLorenz4Pair> { enum { value = 4 }; };
+template <> struct StepMinBlocks<EnvHRSync> { enum { value = 4 }; };
+template <> struct StepMinBlocks<EnvPMSMSync> { enum { value = 5 }; };
+template <> struct StepMinBlocks<EnvPMSMClassic> { enum { value = 4 }; };
+template <> struct StepMinBlocks<EnvPMSMSingle> { enum { value = 4 }; };
+template <> struct StepMinBlocks<EnvMemristive4Pair> { enum { value = 4 }; };
+template <> struct StepMinBlocks<EnvPMSMFree> { enum { value = 5 }; };
+
 }  // namespace cl

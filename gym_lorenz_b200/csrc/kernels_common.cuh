@@ -224,6 +224,12 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
                                              const float* a, const bool want_noise, const bool obs64,
                                              const bool autoreset, unsigned& bad_acc, float* sm_rows, bool& fin) {
   typedef typename E::real real;
+  // The per-interval Philox stream (key / counter words).  Generic kernels build it up front: building
+  // it inside the noise and reset branches instead measured -10 % on the HR single-step kernel at
+  // 1 Mi envs (-5 % pmsm_classic).  The plain rollout kernels build it only when an episode ends:
+  // their interval loop is short of uniform registers (see PlainRollout) and has no noise draw.
+  Stream rng = {};
+  if (!PLAIN) rng = make_stream(p, i, step);
   double nz[E::NOISE > 0 ? E::NOISE : 1];
   nz[0] = 0.0;
   if (want_noise) {
@@ -231,7 +237,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
 #pragma unroll
       for (int c = 0; c < E::NOISE; ++c) nz[c] = live ? p.noise[c * p.n_pad + i] : 0.0;
     } else {
-      draw_normal<(E::NOISE > 0 ? E::NOISE : 1)>(make_stream(p, i, step), TAG_NOISE, nz);
+      draw_normal<(E::NOISE > 0 ? E::NOISE : 1)>(rng, TAG_NOISE, nz);
     }
   }
 
@@ -285,7 +291,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
     if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;   // tested only when an episode ends
     if (p.last_ep_len) p.last_ep_len[i] = ep_len;
     if (autoreset) {
-      E::reset(s, p, make_stream(p, i, step), obs);  // the Philox stream is only built when it is needed
+      E::reset(s, p, PLAIN ? make_stream(p, i, step) : rng, obs);
       ep_len = 0;
       ep_ret = 0.0;
       fin = true;
@@ -327,8 +333,15 @@ __device__ __forceinline__ void synth_action(const KParams& p, const Stream& rng
 
 // ---- the static step / rollout kernel: thread i owns env i for the whole launch ----------
 
+// Resident 256-thread blocks per SM the SINGLE-STEP kernel is compiled for (0 = leave it to ptxas).
+// The parity kinds' single steps are HBM-bound: what counts is bytes in flight, i.e. occupancy, so
+// their register budget is capped at 64 (4 blocks) or 48 (5 blocks) -- measured at 1 Mi envs:
+// hr_sync 0.72 -> 0.76 of the copy bandwidth, pmsm_sync 0.61 -> 0.75, pmsm_classic 0.67 -> 0.68,
+// lorenz3 0.87 -> 0.88; 5 blocks cost lorenz3_pair / lorenz4_pair 2 % (spills), so they stay at 4.
+template <class E> struct StepMinBlocks { enum { value = 0 }; };
+
 template <class E, bool ROLL, bool PLAIN = false>
-__global__ void __launch_bounds__(256) k_step(const KParams p) {
+__global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_step(const KParams p) {
   extern __shared__ __align__(16) float sm_rows_all[];  // [warps per block][32 * OBS], row-store staging
   const int64_t i = p.i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < p.n;
