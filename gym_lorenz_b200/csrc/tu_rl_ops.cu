@@ -176,6 +176,36 @@ extern "C" int cl_obs_moments(void* stream, const float* obs, int64_t es, int64_
   return fail_if(cudaGetLastError());
 }
 
+// Chan et al. parallel update of (mean, var, count) with one batch's shifted sums -- SB3
+// RunningMeanStd.update_from_moments (stable_baselines3/common/running_mean_std.py), the same
+// operations in the same order, entirely on the device: the running count is a device scalar, so
+// a VecNormalize step neither synchronises nor bakes host state into a captured CUDA graph.
+//   acc[0][c] = sum(x - mean_old), acc[1][c] = sum((x - mean_old)^2)   (cl_obs_moments)
+__global__ void k_rms_merge(const double* __restrict__ acc, double n, int dim, double* mean, double* var,
+                            double* count) {
+  const int c = threadIdx.x;
+  const double cnt = *count, tot = cnt + n;
+  if (c < dim) {
+    const double d1 = acc[c] / n;                     // batch_mean - mean
+    const double batch_var = acc[dim + c] / n - d1 * d1;
+    const double batch_mean = mean[c] + d1;
+    const double delta = batch_mean - mean[c];
+    const double new_mean = mean[c] + delta * n / tot;
+    const double m2 = var[c] * cnt + batch_var * n + delta * delta * cnt * n / tot;
+    mean[c] = new_mean;
+    var[c] = m2 / tot;
+  }
+  __syncthreads();  // every thread has read *count
+  if (c == 0) *count = tot;
+}
+
+extern "C" int cl_rms_update(void* stream, const double* acc2d, int64_t n, int32_t dim, double* mean, double* var,
+                             double* count) {
+  if (!acc2d || !mean || !var || !count || dim < 1 || dim > 32 || n < 1) return CL_EINVAL;
+  k_rms_merge<<<1, 32, 0, (cudaStream_t)stream>>>(acc2d, (double)n, dim, mean, var, count);
+  return fail_if(cudaGetLastError());
+}
+
 extern "C" int cl_obs_normalize(void* stream, const float* in, int64_t ies, int64_t ics, float* out, int64_t oes,
                                 int64_t ocs, int64_t n, int32_t dim, const double* mean, const double* var,
                                 double epsilon, double clip) {

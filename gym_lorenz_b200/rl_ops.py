@@ -61,14 +61,24 @@ def eval_metrics(err: torch.Tensor, ctrl: torch.Tensor, dt: float, error_band: f
 
 
 class RunningMeanStd:
-    """SB3 RunningMeanStd (float64 mean/var/count, Chan et al. parallel update) with the batch
-    moments computed on the device."""
+    """SB3 RunningMeanStd (float64 mean/var/count, Chan et al. parallel update).  Batch moments and
+    the merge both run on the device and update `mean` / `var` / `count_t` in place: no host
+    synchronisation, and an `update` can be captured in a CUDA graph and replayed."""
 
     def __init__(self, shape, device, epsilon: float = 1e-4):
         self.mean = torch.zeros(shape, dtype=torch.float64, device=device)
         self.var = torch.ones(shape, dtype=torch.float64, device=device)
-        self.count = float(epsilon)
+        self.count_t = torch.full((1,), float(epsilon), dtype=torch.float64, device=device)
         self._acc = torch.zeros((2,) + tuple(shape), dtype=torch.float64, device=device)
+
+    @property
+    def count(self) -> float:
+        """Host copy of the running count (synchronises; for inspection / checkpoints)."""
+        return float(self.count_t.item())
+
+    @count.setter
+    def count(self, v: float) -> None:
+        self.count_t.fill_(float(v))
 
     def update(self, x: torch.Tensor) -> None:
         """x: f32 [N, dim] (any strides)."""
@@ -76,18 +86,11 @@ class RunningMeanStd:
         n, dim = x.shape
         dev = x.device
         with torch.cuda.device(dev):
-            L.check(lib.cl_obs_moments(_stream(dev), _p(x), x.stride(0), x.stride(1), n, dim, _p(self.mean),
+            st = _stream(dev)
+            L.check(lib.cl_obs_moments(st, _p(x), x.stride(0), x.stride(1), n, dim, _p(self.mean),
                                        _p(self._acc)), None, "cl_obs_moments")
-        d1 = self._acc[0] / n                    # batch_mean - self.mean
-        batch_var = self._acc[1] / n - d1 * d1
-        self.update_from_moments(self.mean + d1, batch_var, n)
-
-    def update_from_moments(self, batch_mean, batch_var, batch_count) -> None:
-        delta = batch_mean - self.mean
-        tot = self.count + batch_count
-        new_mean = self.mean + delta * batch_count / tot
-        m2 = self.var * self.count + batch_var * batch_count + delta * delta * self.count * batch_count / tot
-        self.mean, self.var, self.count = new_mean, m2 / tot, tot
+            L.check(lib.cl_rms_update(st, _p(self._acc), n, dim, _p(self.mean), _p(self.var), _p(self.count_t)),
+                    None, "cl_rms_update")
 
 
 class DeviceVecNormalize:
@@ -145,10 +148,10 @@ class DeviceVecNormalize:
             self.obs_rms.update(obs)
         nobs = self.normalize_obs(obs, self._out)
         if self.training and self.norm_reward:
-            self.returns = self.returns * self.gamma + rew.double()
+            self.returns.mul_(self.gamma).add_(rew)      # in place: replayable as a captured graph
             self.ret_rms.update(self.returns.float().view(-1, 1))
         nrew = self.normalize_reward(rew)
-        self.returns = torch.where(done != 0, torch.zeros_like(self.returns), self.returns)
+        self.returns.masked_fill_(done != 0, 0.0)
         return nobs, nrew, done
 
     def terminal_obs(self) -> torch.Tensor:
@@ -163,8 +166,8 @@ class DeviceVecNormalize:
                 "ret_var": self.ret_rms.var.clone(), "ret_count": self.ret_rms.count}
 
     def load_state_dict(self, sd):
-        self.obs_rms.mean, self.obs_rms.var, self.obs_rms.count = sd["obs_mean"].clone(), sd["obs_var"].clone(), sd["obs_count"]
-        self.ret_rms.mean, self.ret_rms.var, self.ret_rms.count = sd["ret_mean"].clone(), sd["ret_var"].clone(), sd["ret_count"]
+        for rms, k in ((self.obs_rms, "obs"), (self.ret_rms, "ret")):   # in place: captured graphs keep pointing here
+            rms.mean.copy_(sd[k + "_mean"]); rms.var.copy_(sd[k + "_var"]); rms.count = sd[k + "_count"]
 
 
 class DeviceVecFrameStack:

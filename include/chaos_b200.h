@@ -291,6 +291,11 @@ int cl_gae(void* stream, const float* rewards, const float* values, const float*
  * obs addressed obs[i*es + c*cs] like cl_io. */
 int cl_obs_moments(void* stream, const float* obs, int64_t es, int64_t cs, int64_t n, int32_t dim,
                    const double* shift, double* out2d);
+/* RunningMeanStd.update_from_moments on the device (SB3 2.7.1 common/running_mean_std.py; used by
+ * VecNormalize, code/lorenz_pmsm/train.py:118): merges the shifted sums cl_obs_moments wrote into
+ * acc2d[2][dim] for a batch of n rows into mean[dim], var[dim] and the device scalar *count. */
+int cl_rms_update(void* stream, const double* acc2d, int64_t n, int32_t dim, double* mean, double* var,
+                  double* count);
 int cl_obs_normalize(void* stream, const float* in, int64_t ies, int64_t ics, float* out, int64_t oes,
                      int64_t ocs, int64_t n, int32_t dim, const double* mean, const double* var,
                      double epsilon, double clip);

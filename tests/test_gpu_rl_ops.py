@@ -204,3 +204,59 @@ def test_cuda_graph_collector_equals_eager_collector():
     assert outs[False][2]["episodes"] == outs[True][2]["episodes"] > 0
     # and the rollouts differ from one another (the streams really advance across replays)
     assert not torch.equal(outs[True][0][0]["obs"], outs[True][0][1]["obs"])
+
+
+def test_vecnormalize_pipeline_replays_as_cuda_graph():
+    """VecNormalize(env) -- the PMSM pipeline of code/lorenz_pmsm/train.py:115-118 -- captured once as a
+    CUDA graph and replayed: running statistics (device-resident count), discounted returns, env
+    state and outputs must equal eager stepping bit for bit."""
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n, per_graph, replays = 4096, 5, 4
+    g0 = torch.Generator(device="cpu").manual_seed(7)
+    acts = (torch.rand((per_graph, n, 2), generator=g0) * 2 - 1).to("cuda:0")
+
+    def make():
+        env = BatchedChaosVecEnv("pmsm_sync", n, seed=5, max_episode_steps=7)
+        vn = rl_ops.DeviceVecNormalize(env, clip_obs=10.0, gamma=0.99)
+        vn.reset_tensor()
+        return env, vn
+
+    env_e, vn_e = make()
+    for r in range(replays):
+        for t in range(per_graph):
+            out_e = vn_e.step_tensor(acts[t])
+    torch.cuda.synchronize()
+
+    env_w, vn_w = make()                      # throw-away twin: warms the kernels up on a side stream
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        vn_w.step_tensor(acts[0])
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    env_w.close()
+
+    env_g, vn_g = make()
+    env_g.batch.set_graph_mode(True)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for t in range(per_graph):
+            out_g = vn_g.step_tensor(acts[t])
+    for r in range(replays):
+        graph.replay()
+    torch.cuda.synchronize()
+    # the batch sums are accumulated with floating-point atomics: their order, hence the last bits of
+    # the statistics, differs from run to run (eager or not) -- everything else is exact
+    assert torch.allclose(out_g[0], out_e[0], rtol=1e-6, atol=1e-6) and torch.allclose(out_g[1], out_e[1], rtol=1e-6)
+    assert torch.equal(out_g[2], out_e[2])
+    for rg, re_ in ((vn_g.obs_rms, vn_e.obs_rms), (vn_g.ret_rms, vn_e.ret_rms)):
+        assert torch.allclose(rg.mean, re_.mean, rtol=1e-12, atol=1e-13) and torch.allclose(rg.var, re_.var, rtol=1e-12)
+        assert rg.count == re_.count
+    assert vn_e.obs_rms.count == pytest.approx(1e-4 + n * (1 + per_graph * replays))
+    assert torch.equal(vn_g.returns, vn_e.returns)      # raw rewards: independent of the statistics
+    assert torch.equal(env_g.batch.state, env_e.batch.state)
+    assert env_g.batch.stats()["episodes"] == env_e.batch.stats()["episodes"] > 0
+    env_g.batch.set_graph_mode(False)
+    env_g.close(); env_e.close()
