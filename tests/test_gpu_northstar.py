@@ -292,3 +292,65 @@ def test_plain_rollout_instantiation_equals_generic_bitwise(kind, n, T, monkeypa
         assert a[6][key] == c[6][key], key
     assert a[6]["episodes"] > 0
     assert np.isclose(a[6]["return_sum"], c[6]["return_sum"], rtol=1e-12)   # atomics: order differs
+
+
+@pytest.mark.parametrize("kind", ["lorenz_rk4", "lorenz_rk4_f32"])
+def test_one_mebi_envs_per_gpu_properties(kind, oracle_api):
+    """BASELINE configs[3] size (1,048,576 envs per GPU, FP64 and FP32): size-independent properties.
+    (a) sharding invariance: 8 slabs of 131,072 envs with env_id_base = r * 131,072 (what 8 ranks
+        own) reproduce the single 1 Mi batch bit for bit -- reset states and a fused rollout with
+        auto-resets inside; (b) the fused rollout equals single steps; (c) sum of rewards equals the
+        Monitor return of finished episodes; (d) a 4,096-env sample of the big batch equals the
+        oracle run on just those envs (same global env ids)."""
+    import torch
+    O = oracle_api
+    n, shards, T = 1 << 20, 8, 6
+    kw = dict(seed=13, autoreset=True, max_episode_steps=4, substeps=16)
+    full = H.gpu_batch(kind, n, **kw)
+    full.reset()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    acts = (torch.rand((T, full.act_dim, n), generator=g) * 2 - 1).to(full.device)        # SoA, env stride 1
+    st0 = full.state.clone()
+    out = full.rollout(T, acts.permute(0, 2, 1))
+    assert full.plain_launch_count == 1
+    per = n // shards
+    for r in range(shards):
+        sl = slice(r * per, (r + 1) * per)
+        h = H.gpu_batch(kind, per, env_id_base=r * per, **kw)
+        h.reset()
+        assert torch.equal(h.state[:, :per], st0[:, sl])
+        if r in (0, 5):
+            oh = h.rollout(T, acts[:, :, sl].permute(0, 2, 1))
+            assert torch.equal(oh["obs"][:, :, :per], out["obs"][:, :, sl])
+            assert torch.equal(oh["reward"][:, :per], out["reward"][:, sl])
+            assert torch.equal(oh["done"][:, :per], out["done"][:, sl])
+            assert torch.equal(h.state[:, :per], full.state[:, sl])
+        h.close()
+    # (b) single steps on a fresh batch
+    b2 = H.gpu_batch(kind, n, **kw)
+    b2.reset()
+    ret = torch.zeros(n, dtype=torch.float64, device=full.device)
+    for t in range(T):
+        obs, rew, done = b2.step(acts[t].t())
+        assert torch.equal(rew, out["reward"][t, :n]) and torch.equal(done, out["done"][t, :n])
+        ret += rew.double()
+        if t == 3:   # (c) every env hits the 4-step TimeLimit here (unless it blew up earlier)
+            fin = done != 0
+            assert fin.all()
+            trunc_only = done == 2
+            assert torch.equal(b2.last_ep_ret[:n][trunc_only], ret[trunc_only])
+            ret.zero_()
+    assert torch.equal(b2.state, full.state)
+    # (d) oracle on a sample: global env ids 777,000 .. 781,095
+    lo, m = 777_000, 4096
+    o = O.Oracle(kind, m, flags=O.F_AUTORESET, seed=13, substeps=16, dt=0.01, act_limit=1.0, act_gain=50.0,
+                 max_episode_steps=4, env_id_base=lo)
+    o.reset()
+    a_np = np.zeros((T, o.act_dim, o.n_pad), np.float32)
+    a_np[:, :, :m] = acts[:, :, lo:lo + m].cpu().numpy()
+    ref = o.rollout(T, a_np)
+    tol = 1e-11 if kind == "lorenz_rk4" else 2e-4
+    H.assert_close(out["reward"][:, lo:lo + m].double().cpu().numpy(), ref["reward"][:, :m], tol, "reward vs oracle", atol=tol)
+    assert np.array_equal(out["done"][:, lo:lo + m].cpu().numpy(), ref["done"][:, :m])
+    H.assert_close(full.state[:3, lo:lo + m].double().cpu().numpy(), o.state[:3, :m], tol, "state vs oracle", atol=tol)
+    full.close(); b2.close()
