@@ -354,3 +354,39 @@ def test_one_mebi_envs_per_gpu_properties(kind, oracle_api):
     assert np.array_equal(out["done"][:, lo:lo + m].cpu().numpy(), ref["done"][:, :m])
     H.assert_close(full.state[:3, lo:lo + m].double().cpu().numpy(), o.state[:3, :m], tol, "state vs oracle", atol=tol)
     full.close(); b2.close()
+
+
+@pytest.mark.parametrize("kind", ["lorenz_rk4", "hr_sync", "lorenz_rk4_f32"])
+@pytest.mark.parametrize("layout", ["planes", "rows"])
+def test_rollout_outputs_stay_inside_their_buffers(kind, layout):
+    """Guard bands around every rollout output (ragged batch: partial last warp, N not a multiple of
+    the 128-env padding): the vectorised row stores / plane stores must not touch a byte outside
+    [T, ...] -- the check compute-sanitizer would do, written as a test."""
+    import torch
+    n, T, G = 1000 + 13, 7, 4096
+    b = H.gpu_batch(kind, n, seed=3, autoreset=True, max_episode_steps=3)
+    b.reset()
+    NP, O = b.n_pad, b.obs_dim
+    shape = (T, n, O) if layout == "rows" else (T, O, NP)
+    numel = int(np.prod(shape))
+    raw = {"obs": torch.full((numel + 2 * G,), 12345.0, dtype=torch.float32, device=b.device),
+           "reward": torch.full((T * NP + 2 * G,), 12345.0, dtype=b.real, device=b.device),
+           "done": torch.full((T * NP + 2 * G,), 77, dtype=torch.uint8, device=b.device)}
+    out = {"obs": raw["obs"][G:G + numel].view(shape), "reward": raw["reward"][G:G + T * NP].view(T, NP),
+           "done": raw["done"][G:G + T * NP].view(T, NP)}
+    g = torch.Generator(device="cpu").manual_seed(1)
+    acts = (torch.rand((T, b.act_dim, NP), generator=g) * 2 - 1).to(b.device)
+    for dyn in ("0", "1"):
+        import os
+        os.environ["CHAOS_B200_DYN"] = dyn
+        try:
+            b.rollout(T, acts[:, :, :n].permute(0, 2, 1), out=out, obs_layout=layout)
+        finally:
+            os.environ.pop("CHAOS_B200_DYN", None)
+        torch.cuda.synchronize()
+        for k, fill in (("obs", 12345.0), ("reward", 12345.0), ("done", 77)):
+            assert bool((raw[k][:G] == fill).all()) and bool((raw[k][-G:] == fill).all()), (k, dyn)
+        if layout == "planes":   # padding lanes n .. n_pad of every plane are never written either
+            assert bool((out["obs"][:, :, n:] == 12345.0).all()) and bool((out["done"][:, n:] == 77).all())
+        assert bool(torch.isfinite(out["obs"][..., :n] if layout == "planes" else out["obs"]).all())
+    b.close()

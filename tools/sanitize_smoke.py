@@ -30,12 +30,12 @@ for kind in ("lorenz3", "lorenz3_pair", "lorenz4_pair", "hr_sync", "pmsm_sync", 
         os.environ.pop("CHAOS_B200_DYN", None)
         b.stats()
         b.close()
-for zc in ("1", "0"):
-    os.environ["CHAOS_B200_ZEROCOPY"] = zc
+for mode, slices in (("zerocopy", 1), ("dma", 1), ("pipelined", 3)):
     env = BatchedChaosVecEnv("hr_sync", 777, max_episode_steps=2)
+    env.batch.set_host_mode(mode, slices)
     env.reset()
     for _ in range(5):
-        obs, rew, dones, infos = env.step(np.zeros((777, 2), np.float32))
+        obs, rew, dones, infos = env.step(np.zeros((777, 2), np.float32))   # episodes end: term_obs rows to the host slot
         _ = [d for d in infos if d]
     env.close()
 r = torch.randn((16, 500), device=dev)
