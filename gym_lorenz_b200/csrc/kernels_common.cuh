@@ -194,13 +194,14 @@ __device__ __forceinline__ void store_obs_rows_warp(float* __restrict__ sm, floa
 // ---- one control interval of one env (shared by the static and the dynamic kernels) ----
 
 // The "plain rollout" I/O shape -- what a synthetic-action benchmark or a device-side collector
-// uses: canonical time-major float32 observation planes [T][OBS][n_pad], reward [T][n_pad] in the env's real type, done
-// flags, auto-reset on, no terminal-observation buffer, actions given (staged by
-// bulk copies in the dynamic kernel).  For the kinds whose rollout is arithmetic / issue bound
+// uses: canonical time-major float32 observation planes [T][OBS][n_pad], reward [T][n_pad] in the
+// env's real type, done flags, auto-reset on, no terminal-observation buffer, actions given (staged
+// by bulk copies in the dynamic kernel).  For the kinds whose rollout is arithmetic / issue bound
 // (PlainRollout<E>::value) the rollout kernels are instantiated a second time with these as
 // compile-time facts: the generic interval executes ~245 non-FP64 instructions per warp (runtime
 // layout / null-pointer tests, 64-bit stride arithmetic), the plain one under half of that, and
-// with only ~3 warps per scheduler every epilogue instruction shows (-5 % launch time at 65,536 envs).
+// with only ~3 warps per scheduler every epilogue instruction shows (-3 % launch time at 65,536 envs
+// for FP64, -12...17 % for the issue-bound FP32 kind).
 // launch_env() picks the instantiation from the launch parameters; results are identical.
 template <class E> struct PlainRollout { enum { value = 0 }; };
 template <int N> struct SpecTag { enum { value = N }; };
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
 // static thread<->env mapping leaves every scheduler waiting for the ones that hold 4 (86.5 %
 // balance; partial warps cost a full FP64 issue, tools/dfma_probe.cu).  Here the launch is cut
 // into tasks (env-warp e, chunk c of `dyn_chunk` control intervals); persistent worker warps
-// (4 per scheduler) pull tasks from an atomic counter in c-major order.  Chunk c of an env-warp
+// (3 per scheduler at 65,536 envs: fewer workers than env-warps) pull tasks from an atomic counter in c-major order.  Chunk c of an env-warp
 // may only start after chunk c-1 finished (possibly on another SM): the finishing warp publishes
 // progress[e] with a release store after a device-scope fence, the next one acquires it and
 // reads the state planes with L1-bypassing loads.  A waiting warp only ever waits for a task
