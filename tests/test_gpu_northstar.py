@@ -33,7 +33,7 @@ def test_lorenz_rk4_per_interval_vs_oracle(oracle_api):
 def test_lorenz_rk4_vs_scipy_dop853():
     import torch
     from scipy.integrate import solve_ivp
-    n = 32
+    n = 256
     b = H.gpu_batch("lorenz_rk4", n, seed=3, substeps=16, autoreset=False, max_episode_steps=0)
     b.reset()
     # move onto the attractor first (200 uncontrolled intervals)
@@ -263,7 +263,8 @@ def test_row_major_observation_rollout_equals_plane_layout(kind, n, monkeypatch)
         assert torch.equal(torch.nan_to_num(planes[:, :, :n].permute(0, 2, 1)), torch.nan_to_num(rows))
 
 
-@pytest.mark.parametrize("kind,n,T", [("lorenz_rk4", 65536 + 40, 40), ("pmsm_rk4", 9000, 19), ("lorenz_rk4", 3000, 21),
+@pytest.mark.parametrize("kind,n,T", [("lorenz_rk4", 65536 + 40, 40), ("lorenz_rk4", 65536 + 40, 19),   # 19: partial last chunk
+                                      ("pmsm_rk4", 9000, 19), ("lorenz_rk4", 3000, 21),
                                       ("lorenz_rk4_f32", 65536 + 40, 24), ("lorenz_rk4_f32", 5000, 11)])
 def test_plain_rollout_instantiation_equals_generic_bitwise(kind, n, T, monkeypatch):
     """The rollout kernels exist twice for the FP64-bound kinds: generic, and with the plain I/O
