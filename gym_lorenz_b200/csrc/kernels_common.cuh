@@ -206,6 +206,45 @@ __device__ __forceinline__ void store_obs_rows_warp(float* __restrict__ sm, floa
 template <class E> struct PlainRollout { enum { value = 0 }; };
 template <int N> struct SpecTag { enum { value = N }; };
 
+// ---- deferred outputs of the plain rollout loop -------------------------------------------
+// With ~3 warps per scheduler a warp that is busy converting / addressing / storing its outputs is
+// a warp that feeds no DFMA (the pipe idles whenever none of the few resident warps is eligible).
+// The plain loop therefore keeps the outputs of interval t in registers and emits them at the top
+// of interval t+1, as branch-free predicated stores in the SAME basic block as that interval's
+// integrator, so ptxas interleaves them with the DFMA stream (they only take issue slots, of
+// which half are free).  Terminations and resets are still decided at the end of interval t.
+#ifndef CL_PLAIN_DEFER
+#define CL_PLAIN_DEFER 1
+#endif
+template <class E> struct PlainPending {
+  typename E::real obs[E::OBS];
+  typename E::real rew;
+  uint32_t dflags, valid;
+  int t;
+};
+__device__ __forceinline__ void st_if(float* ptr, float v, uint32_t pr) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n@p st.global.f32 [%1], %2;\n}" ::"r"(pr), "l"(ptr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_if(double* ptr, double v, uint32_t pr) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n@p st.global.f64 [%1], %2;\n}" ::"r"(pr), "l"(ptr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_if(uint8_t* ptr, uint32_t v, uint32_t pr) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n@p st.global.u8 [%1], %2;\n}" ::"r"(pr), "l"(ptr), "r"(v) : "memory");
+}
+template <class E>
+__device__ __forceinline__ void plain_emit(const KParams& p, const int64_t i, const bool live, const PlainPending<E>& d) {
+  typedef typename E::real real;
+  const uint32_t pr = (live && d.valid) ? 1u : 0u;
+  // canonical time-major planes obs[T][OBS][n_pad], reward[T][n_pad], done[T][n_pad]: every stride
+  // derives from n_pad (uniform registers are scarce in this loop, see PlainRollout); i < n_pad always
+  const int64_t np = p.n_pad, row = (int64_t)d.t * np + i;
+  float* o = (float*)p.obs + (int64_t)d.t * (E::OBS * np) + i;
+#pragma unroll
+  for (int c = 0; c < E::OBS; ++c) st_if(o + c * np, (float)d.obs[c], pr);
+  st_if((real*)p.reward + row, d.rew, pr);
+  st_if(p.done + row, d.dflags, pr);
+}
+
 // SPEC: warp-uniform specialisation of E::step chosen once per launch / task (0 = generic).  Kinds
 // with PlainRollout<E>::value provide `static int spec(const S&, const KParams&)` (evaluated by all
 // 32 lanes) and `template <int SPEC> step_spec(...)`; the plain rollout kernels then run one of two
@@ -223,8 +262,10 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
                                              const KParams& p, const int64_t i, const bool live,
                                              const unsigned lane, const int t, const uint64_t step,
                                              const float* a, const bool want_noise, const bool obs64,
-                                             const bool autoreset, unsigned& bad_acc, float* sm_rows, bool& fin) {
+                                             const bool autoreset, unsigned& bad_acc, float* sm_rows, bool& fin,
+                                             PlainPending<E>* pend = nullptr) {
   typedef typename E::real real;
+  if (PLAIN && CL_PLAIN_DEFER) plain_emit<E>(p, i, live, *pend);   // outputs of the previous interval
   // The per-interval Philox stream (key / counter words).  Generic kernels build it up front: building
   // it inside the noise and reset branches instead measured -10 % on the HR single-step kernel at
   // 1 Mi envs (-5 % pmsm_classic).  The plain rollout kernels build it only when an episode ends:
@@ -303,9 +344,9 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
     store_obs_rows_warp<real, E::OBS>(sm_rows, (float*)p.obs + oo, i - (int64_t)lane, p.n, lane, obs);
   if (live) {
     const uint8_t dflags = (uint8_t)((term ? CL_DONE_TERMINATED : 0) | (trunc ? CL_DONE_TRUNCATED : 0));
-    if (PLAIN) {
-      // canonical time-major planes obs[T][OBS][n_pad], reward[T][n_pad], done[T][n_pad]: every
-      // stride derives from n_pad (uniform registers are scarce in this loop, see PlainRollout)
+    if (PLAIN && CL_PLAIN_DEFER) {
+      // emitted at the top of the next interval (or by the caller after the last one)
+    } else if (PLAIN) {
       const int64_t np = p.n_pad, row = (int64_t)t * np + i;
       float* o = (float*)p.obs + (int64_t)t * (E::OBS * np) + i;
 #pragma unroll
@@ -321,6 +362,14 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
       }
       if (p.done) p.done[(ROLL ? t * p.done_ts : 0) + i] = dflags;
     }
+  }
+  if (PLAIN && CL_PLAIN_DEFER) {
+#pragma unroll
+    for (int c = 0; c < E::OBS; ++c) pend->obs[c] = obs[c];
+    pend->rew = rew;
+    pend->dflags = (uint32_t)((term ? CL_DONE_TERMINATED : 0) | (trunc ? CL_DONE_TRUNCATED : 0));
+    pend->t = t;
+    pend->valid = 1u;
   }
 }
 
@@ -374,6 +423,10 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
   unsigned bad_acc = 0u;
   bool fin = E::finite(s);
   const uint64_t step0 = step_base(p);
+  PlainPending<E> pend;
+  pend.valid = 0u; pend.t = 0; pend.dflags = 0u; pend.rew = 0;
+#pragma unroll
+  for (int c = 0; c < E::OBS; ++c) pend.obs[c] = 0;
   auto intervals = [&](auto spec_tag) {
     constexpr int SPEC = decltype(spec_tag)::value;
     for (int t = 0; t < T; ++t) {
@@ -390,12 +443,13 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
             a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
         }
       }
-      env_interval<E, ROLL, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin);
+      env_interval<E, ROLL, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin, &pend);
     }
   };
   if constexpr (PLAIN) {
     if (E::spec(s, p) == 1) intervals(SpecTag<1>{});
     else intervals(SpecTag<0>{});
+    if (CL_PLAIN_DEFER) plain_emit<E>(p, i, live, pend);   // the last interval's outputs
   } else {
     intervals(SpecTag<0>{});
   }
@@ -545,6 +599,10 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     const float* ab = abuf;
     unsigned bad_acc = 0u;
     bool fin = E::finite(s);
+    PlainPending<E> pend;
+    pend.valid = 0u; pend.t = 0; pend.dflags = 0u; pend.rew = 0;
+#pragma unroll
+    for (int c = 0; c < E::OBS; ++c) pend.obs[c] = 0;
     auto intervals = [&](auto spec_tag) {
       constexpr int SPEC = decltype(spec_tag)::value;
       for (int tl = 0; tl < len; ++tl) {
@@ -561,12 +619,13 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
           for (int cc = 0; cc < E::ACT; ++cc)
             a[cc] = live ? p.action[(int64_t)t * p.act_ts + i * p.act_es + cc * p.act_cs] : 0.0f;
         }
-        env_interval<E, true, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin);
+        env_interval<E, true, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin, &pend);
       }
     };
     if constexpr (PLAIN) {
       if (E::spec(s, p) == 1) intervals(SpecTag<1>{});
       else intervals(SpecTag<0>{});
+      if (CL_PLAIN_DEFER) plain_emit<E>(p, i, live, pend);   // the task's last interval
     } else {
       intervals(SpecTag<0>{});
     }
