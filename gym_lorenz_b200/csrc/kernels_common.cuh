@@ -506,9 +506,21 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+
+#ifndef CL_DYN_EMIT_AFTER_RELEASE
+#define CL_DYN_EMIT_AFTER_RELEASE 1
+#endif
+#ifndef CL_DYN_LDACQ
+#define CL_DYN_LDACQ 1
+#endif
 
 template <class E, bool PLAIN = false>
 __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
@@ -578,8 +590,12 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
       // per-env loads below additionally bypass L1; dropping the fence measured only +0.7 %, so
       // the formally synchronised version is kept.)
       if (lane == 0) {
+#if CL_DYN_LDACQ
+        while (ld_acquire_u32(p.dyn_progress + e) < c) __nanosleep(32);   // orders the loads below, waits for no store
+#else
         while (ld_relaxed_u32(p.dyn_progress + e) < c) __nanosleep(32);
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
       }
       __syncwarp();
     }
@@ -625,7 +641,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     if constexpr (PLAIN) {
       if (E::spec(s, p) == 1) intervals(SpecTag<1>{});
       else intervals(SpecTag<0>{});
-      if (CL_PLAIN_DEFER) plain_emit<E>(p, i, live, pend);   // the task's last interval
+      if (CL_PLAIN_DEFER && !CL_DYN_EMIT_AFTER_RELEASE) plain_emit<E>(p, i, live, pend);   // the task's last interval
     } else {
       intervals(SpecTag<0>{});
     }
@@ -639,6 +655,11 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     // publish: the warp barrier orders every lane's stores before lane 0's release store
     __syncwarp();
     if (lane == 0) st_release_u32(p.dyn_progress + e, c + 1u);
+    if constexpr (PLAIN) {
+      // the last interval's output streams go out AFTER the hand-off: the release only has to wait
+      // for the state planes (nobody reads the output streams through `progress`)
+      if (CL_PLAIN_DEFER && CL_DYN_EMIT_AFTER_RELEASE) plain_emit<E>(p, i, live, pend);
+    }
     q = grab();
   }
 }
