@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
 // into tasks (env-warp e, chunk c of `dyn_chunk` control intervals); persistent worker warps
 // (3 per scheduler at 65,536 envs: fewer workers than env-warps) pull tasks from an atomic counter in c-major order.  Chunk c of an env-warp
 // may only start after chunk c-1 finished (possibly on another SM): the finishing warp publishes
-// progress[e] with a release store after a device-scope fence, the next one acquires it and
+// progress[e] with a release store, the next one reads it with an acquire load and
 // reads the state planes with L1-bypassing loads.  A waiting warp only ever waits for a task
 // with a smaller index, which some running (or finished) warp already owns, so the scheme cannot
 // deadlock whatever the residency.
@@ -501,11 +501,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -514,13 +509,6 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
-#ifndef CL_DYN_EMIT_AFTER_RELEASE
-#define CL_DYN_EMIT_AFTER_RELEASE 1
-#endif
-#ifndef CL_DYN_LDACQ
-#define CL_DYN_LDACQ 1
-#endif
 
 template <class E, bool PLAIN = false>
 __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
@@ -586,16 +574,12 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
       stage(q, 0);
     }
     if (c > 0) {
-      // relaxed polling, then one acquire fence: pairs with the writer's release store.  (All
-      // per-env loads below additionally bypass L1; dropping the fence measured only +0.7 %, so
-      // the formally synchronised version is kept.)
+      // acquire load: pairs with the writer's release store and orders the state loads below after
+      // it, without waiting for this warp's own outstanding output stores (a fence.acq_rel would).
+      // The warp barrier extends the ordering from lane 0 to the other lanes; all per-env loads
+      // additionally bypass L1.
       if (lane == 0) {
-#if CL_DYN_LDACQ
-        while (ld_acquire_u32(p.dyn_progress + e) < c) __nanosleep(32);   // orders the loads below, waits for no store
-#else
-        while (ld_relaxed_u32(p.dyn_progress + e) < c) __nanosleep(32);
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-#endif
+        while (ld_acquire_u32(p.dyn_progress + e) < c) __nanosleep(32);
       }
       __syncwarp();
     }
@@ -641,7 +625,6 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     if constexpr (PLAIN) {
       if (E::spec(s, p) == 1) intervals(SpecTag<1>{});
       else intervals(SpecTag<0>{});
-      if (CL_PLAIN_DEFER && !CL_DYN_EMIT_AFTER_RELEASE) plain_emit<E>(p, i, live, pend);   // the task's last interval
     } else {
       intervals(SpecTag<0>{});
     }
@@ -658,7 +641,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     if constexpr (PLAIN) {
       // the last interval's output streams go out AFTER the hand-off: the release only has to wait
       // for the state planes (nobody reads the output streams through `progress`)
-      if (CL_PLAIN_DEFER && CL_DYN_EMIT_AFTER_RELEASE) plain_emit<E>(p, i, live, pend);
+      if (CL_PLAIN_DEFER) plain_emit<E>(p, i, live, pend);
     }
     q = grab();
   }
