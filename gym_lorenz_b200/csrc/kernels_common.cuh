@@ -220,7 +220,24 @@ template <class E> struct PlainPending {
   typename E::real obs[E::OBS];
   typename E::real rew;
   uint32_t dflags, valid;
-  int t;
+  int t;   // interval the record belongs to (addressing of the static kernel)
+  // Dynamic kernel: running output pointers of this lane, bumped by one time step per emit --
+  // recomputing t * stride + i with 64-bit arithmetic costs ~20 more integer instructions per
+  // interval (+1.3 % FP64, +2.6 % FP32 at 65,536 envs).  The static kernel keeps the recomputation:
+  // at 1 Mi envs it lives on occupancy and the six extra registers cost the FP32 kind 3 %.
+  float* o;
+  typename E::real* rp;
+  uint8_t* dp;
+  __device__ __forceinline__ void begin(const KParams& p, const int64_t i, const int t0) {
+    const int64_t np = p.n_pad, row = (int64_t)t0 * np + i;   // i < n_pad always
+    o = (float*)p.obs + (int64_t)t0 * (E::OBS * np) + i;
+    rp = (typename E::real*)p.reward + row;
+    dp = p.done + row;
+    t = t0;
+    valid = 0u; dflags = 0u; rew = 0;
+#pragma unroll
+    for (int c = 0; c < E::OBS; ++c) obs[c] = 0;
+  }
 };
 __device__ __forceinline__ void st_if(float* ptr, float v, uint32_t pr) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n@p st.global.f32 [%1], %2;\n}" ::"r"(pr), "l"(ptr), "f"(v) : "memory");
@@ -231,18 +248,31 @@ __device__ __forceinline__ void st_if(double* ptr, double v, uint32_t pr) {
 __device__ __forceinline__ void st_if(uint8_t* ptr, uint32_t v, uint32_t pr) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %0, 0;\n@p st.global.u8 [%1], %2;\n}" ::"r"(pr), "l"(ptr), "r"(v) : "memory");
 }
-template <class E>
-__device__ __forceinline__ void plain_emit(const KParams& p, const int64_t i, const bool live, const PlainPending<E>& d) {
+template <class E, bool RUNPTR>
+__device__ __forceinline__ void plain_emit(const KParams& p, const int64_t i, const bool live, PlainPending<E>& d) {
   typedef typename E::real real;
   const uint32_t pr = (live && d.valid) ? 1u : 0u;
   // canonical time-major planes obs[T][OBS][n_pad], reward[T][n_pad], done[T][n_pad]: every stride
-  // derives from n_pad (uniform registers are scarce in this loop, see PlainRollout); i < n_pad always
-  const int64_t np = p.n_pad, row = (int64_t)d.t * np + i;
-  float* o = (float*)p.obs + (int64_t)d.t * (E::OBS * np) + i;
+  // derives from n_pad (uniform registers are scarce in this loop, see PlainRollout)
+  const int64_t np = p.n_pad;
+  if (RUNPTR) {
 #pragma unroll
-  for (int c = 0; c < E::OBS; ++c) st_if(o + c * np, (float)d.obs[c], pr);
-  st_if((real*)p.reward + row, d.rew, pr);
-  st_if(p.done + row, d.dflags, pr);
+    for (int c = 0; c < E::OBS; ++c) st_if(d.o + c * np, (float)d.obs[c], pr);
+    st_if(d.rp, d.rew, pr);
+    st_if(d.dp, d.dflags, pr);
+    if (d.valid) {   // warp-uniform; the first emit of a task is the empty one and must not move
+      d.o += E::OBS * np;
+      d.rp += np;
+      d.dp += np;
+    }
+  } else {
+    const int64_t row = (int64_t)d.t * np + i;   // i < n_pad always
+    float* o = (float*)p.obs + (int64_t)d.t * (E::OBS * np) + i;
+#pragma unroll
+    for (int c = 0; c < E::OBS; ++c) st_if(o + c * np, (float)d.obs[c], pr);
+    st_if((real*)p.reward + row, d.rew, pr);
+    st_if(p.done + row, d.dflags, pr);
+  }
 }
 
 // SPEC: warp-uniform specialisation of E::step chosen once per launch / task (0 = generic).  Kinds
@@ -257,7 +287,7 @@ __device__ __forceinline__ void step_dispatch(typename E::S& s, const KParams& p
   else E::step(s, p, a, nz, obs, rew, term);
 }
 
-template <class E, bool ROLL, bool PLAIN = false, int SPEC = 0>
+template <class E, bool ROLL, bool PLAIN = false, int SPEC = 0, bool RUNPTR = false>
 __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, double& ep_ret,
                                              const KParams& p, const int64_t i, const bool live,
                                              const unsigned lane, const int t, const uint64_t step,
@@ -265,7 +295,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
                                              const bool autoreset, unsigned& bad_acc, float* sm_rows, bool& fin,
                                              PlainPending<E>* pend = nullptr) {
   typedef typename E::real real;
-  if (PLAIN && CL_PLAIN_DEFER) plain_emit<E>(p, i, live, *pend);   // outputs of the previous interval
+  if (PLAIN && CL_PLAIN_DEFER) plain_emit<E, RUNPTR>(p, i, live, *pend);   // outputs of the previous interval
   // The per-interval Philox stream (key / counter words).  Generic kernels build it up front: building
   // it inside the noise and reset branches instead measured -10 % on the HR single-step kernel at
   // 1 Mi envs (-5 % pmsm_classic).  The plain rollout kernels build it only when an episode ends:
@@ -424,9 +454,7 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
   bool fin = E::finite(s);
   const uint64_t step0 = step_base(p);
   PlainPending<E> pend;
-  pend.valid = 0u; pend.t = 0; pend.dflags = 0u; pend.rew = 0;
-#pragma unroll
-  for (int c = 0; c < E::OBS; ++c) pend.obs[c] = 0;
+  pend.begin(p, i, 0);
   auto intervals = [&](auto spec_tag) {
     constexpr int SPEC = decltype(spec_tag)::value;
     for (int t = 0; t < T; ++t) {
@@ -449,7 +477,7 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
   if constexpr (PLAIN) {
     if (E::spec(s, p) == 1) intervals(SpecTag<1>{});
     else intervals(SpecTag<0>{});
-    if (CL_PLAIN_DEFER) plain_emit<E>(p, i, live, pend);   // the last interval's outputs
+    if (CL_PLAIN_DEFER) plain_emit<E, false>(p, i, live, pend);   // the last interval's outputs
   } else {
     intervals(SpecTag<0>{});
   }
@@ -600,9 +628,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     unsigned bad_acc = 0u;
     bool fin = E::finite(s);
     PlainPending<E> pend;
-    pend.valid = 0u; pend.t = 0; pend.dflags = 0u; pend.rew = 0;
-#pragma unroll
-    for (int c = 0; c < E::OBS; ++c) pend.obs[c] = 0;
+    pend.begin(p, i, t0);
     auto intervals = [&](auto spec_tag) {
       constexpr int SPEC = decltype(spec_tag)::value;
       for (int tl = 0; tl < len; ++tl) {
@@ -619,7 +645,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
           for (int cc = 0; cc < E::ACT; ++cc)
             a[cc] = live ? p.action[(int64_t)t * p.act_ts + i * p.act_es + cc * p.act_cs] : 0.0f;
         }
-        env_interval<E, true, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin, &pend);
+        env_interval<E, true, PLAIN, SPEC, true>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin, &pend);
       }
     };
     if constexpr (PLAIN) {
@@ -641,7 +667,7 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
     if constexpr (PLAIN) {
       // the last interval's output streams go out AFTER the hand-off: the release only has to wait
       // for the state planes (nobody reads the output streams through `progress`)
-      if (CL_PLAIN_DEFER) plain_emit<E>(p, i, live, pend);
+      if (CL_PLAIN_DEFER) plain_emit<E, true>(p, i, live, pend);
     }
     q = grab();
   }
