@@ -207,12 +207,13 @@ template <class E> struct PlainRollout { enum { value = 0 }; };
 template <int N> struct SpecTag { enum { value = N }; };
 
 // ---- deferred outputs of the plain rollout loop -------------------------------------------
-// With ~3 warps per scheduler a warp that is busy converting / addressing / storing its outputs is
-// a warp that feeds no DFMA (the pipe idles whenever none of the few resident warps is eligible).
-// The plain loop therefore keeps the outputs of interval t in registers and emits them at the top
-// of interval t+1, as branch-free predicated stores in the SAME basic block as that interval's
-// integrator, so ptxas interleaves them with the DFMA stream (they only take issue slots, of
-// which half are free).  Terminations and resets are still decided at the end of interval t.
+// The plain loop keeps the outputs of interval t in registers and emits them at the top of interval
+// t+1 as branch-free predicated stores (inline PTX `@p st`): no divergent `if (live)` region with
+// its reconvergence barrier, conversions and address arithmetic in the same basic block as the
+// action fetch and the integrator.  ptxas still schedules them ahead of the DFMA stream rather
+// than into it; measured neutral for FP64 and +5.4 % for the issue-bound FP32 kind at 65,536 envs.
+// It also lets the dynamic kernel hand an env-warp over BEFORE its last outputs go out.
+// Terminations and resets are still decided at the end of interval t.
 #ifndef CL_PLAIN_DEFER
 #define CL_PLAIN_DEFER 1
 #endif
