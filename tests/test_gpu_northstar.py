@@ -1,6 +1,8 @@
 """North-star kinds on the GPU: RK4 x S vs the oracle (1e-12 per interval), vs scipy DOP853
 (1e-9, the tolerance BASELINE.json states), fused rollout == repeated single steps, f32
 variant, per-env parameter randomisation."""
+import os
+
 import numpy as np
 import pytest
 
@@ -286,7 +288,9 @@ def test_plain_rollout_instantiation_equals_generic_bitwise(kind, n, T, monkeypa
         assert b.plain_launch_count == (1 if plain == "1" else 0)
         b.close()
     a, c = outs
-    assert a[7] == c[7] and (a[7] > 0) == (n > 65536)
+    assert a[7] == c[7]
+    if "CHAOS_B200_DYN" not in os.environ:      # automatic choice: dynamic kernel only when env-warps do not divide evenly
+        assert (a[7] > 0) == (n > 65536)
     for k in range(6):
         assert torch.equal(a[k][..., :n], c[k][..., :n]), k
     for key in ("episodes", "length_sum", "terminated", "truncated", "nonfinite_events"):
