@@ -307,6 +307,7 @@ def run_b200(args):
         ach = flops / (kern_ms * 1e-3) * 1e-12
         gbs = float(N) * T * bytes_step / (kern_ms * 1e-3) * 1e-9
         dyn = batch.dyn_launch_count > 0
+        sm_local = batch.sm_launch_count > 0
         plain = ", PLAIN=true" if batch.plain_launch_count > 0 else ""   # which instantiation launch_env picked
         traffic = traffic_detail = None
         try:   # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
@@ -319,14 +320,19 @@ def run_b200(args):
         except Exception:  # noqa: BLE001
             pass
         roofline = {
-            "kernel": (f"cl::k_rollout_dyn<{ENV_TYPE[args.kind]}{plain}> (fused T-interval rollout, env-warp x chunk tasks)" if dyn
+            "kernel": (f"cl::k_rollout_sm<{ENV_TYPE[args.kind]}> (fused T-interval rollout, per-SM queue of env-warp x chunk "
+                       f"tasks, env state in shared memory)" if sm_local
+                       else f"cl::k_rollout_dyn<{ENV_TYPE[args.kind]}{plain}> (fused T-interval rollout, env-warp x chunk tasks)" if dyn
                        else f"cl::k_step<{ENV_TYPE[args.kind]}, ROLL=true{plain}> (fused T-interval rollout)"),
             "bound": "fp64" if fma_bytes == 8 else "fp32", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": ach / fp64_peak if fp64_peak > 0 else None, "traffic": traffic, "traffic_detail": traffic_detail,
             "peak_source": "DFMA-chain micro-kernel (cl_measure_fma_peak) run in this process, 2 flop/FMA; "
                            "MEASURED_PEAKS.json has no FP64 entry",
             "algorithmic_flop_per_substep": flop_sub,
-            "fma_issue_ceiling": 87.0 / (2 * 49),
+            # the integrator works on z - rho (envs_northstar.cuh): 45 FP64-pipe instructions = 82 executed
+            # flop per substep for the 87 algorithmic ones, so the 2-flop-per-FMA ceiling is 87 / 90
+            "executed_fp64_instr_per_substep": 45, "executed_flop_per_substep": 82,
+            "fma_issue_ceiling": 87.0 / (2 * 45),
             "kernel_ms_per_launch": kern_ms,
             "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                     "bytes_per_env_step": bytes_step, "peak_source": hbm_src},

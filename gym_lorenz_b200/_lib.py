@@ -121,6 +121,7 @@ SYMBOLS = [
     ("cl_block_size", C.c_int, [_VP]),
     ("cl_dyn_launch_count", C.c_int64, [_VP]),
     ("cl_plain_launch_count", C.c_int64, [_VP]),
+    ("cl_sm_launch_count", C.c_int64, [_VP]),
     ("cl_gae", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_double, C.c_double, C.c_int32, C.c_int64, C.c_int64, _VP, _VP]),
     ("cl_obs_moments", C.c_int, [_VP, _VP, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _VP, _VP]),
     ("cl_rms_update", C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP]),

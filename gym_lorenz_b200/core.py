@@ -141,6 +141,11 @@ class ChaosBatch:
         return self.lib.cl_plain_launch_count(self.ctx)
 
     @property
+    def sm_launch_count(self) -> int:
+        """Rollouts that ran on the SM-local kernel (k_rollout_sm)."""
+        return self.lib.cl_sm_launch_count(self.ctx)
+
+    @property
     def launch_count(self) -> int:
         return self.lib.cl_launch_count(self.ctx)
 

@@ -93,6 +93,7 @@ struct cl_ctx {
   int no_plain;         // never pick the plain-rollout kernel instantiation
   int64_t dyn_launches;
   int64_t plain_launches;  // rollouts that ran on the plain-I/O kernel instantiation
+  int64_t sm_launches;     // rollouts that ran on the SM-local kernel (k_rollout_sm)
 };
 
 static char g_err[512] = "";
@@ -261,6 +262,8 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
     if (c.kind == CL_ENV_PMSM_RK4) { p.nom[0] = 5.46; p.nom[1] = 20.0; p.nom[2] = 0.0; }
     else { p.nom[0] = 10.0; p.nom[1] = 28.0; p.nom[2] = 8.0 / 3.0; }
     for (int k = 0; k < 3; ++k) p.nomf[k] = (float)p.nom[k];
+    p.nom_br = p.nom[2] * p.nom[1];          // beta * rho, one rounding (see lorenz_rk4)
+    p.nom_brf = p.nomf[2] * p.nomf[1];
     p.act_limit_f = (float)c.act_limit; p.act_gain_f = (float)c.act_gain;
   }
   if (io) {
@@ -283,7 +286,8 @@ static int launch(cl_ctx* ctx, const KParams& p_in, int mode, cudaStream_t st) {
                                            : cl_launch_northstar(ctx->cfg.kind, p, mode, st, ctx->block);
   if (e != cudaSuccess) return fail(ctx, CL_ECUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   ctx->launches += 1;
-  ctx->plain_launches += plain;
+  ctx->plain_launches += (plain & 1);
+  ctx->sm_launches += (plain >> 1) & 1;
   if (ctx->graph_mode && mode != cl::MODE_INIT) {  // device-resident Philox step index (CUDA graphs)
     const uint64_t count = (mode == cl::MODE_ROLLOUT || mode == cl::MODE_ROLLOUT_DYN) ? (uint64_t)p.T : 1;
     k_advance_step<<<1, 1, 0, st>>>(ctx->d_step, count);
@@ -385,6 +389,22 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
       // bulk-copy staging needs unit env stride, 16 B alignment and whole 128 B rows in bounds
       p.dyn_tma = (io->action != nullptr && io->act_es == 1 && (io->act_cs % 4) == 0 && (d->act_ts % 4) == 0 &&
                    ((uintptr_t)io->action % 16) == 0 && io->act_cs >= W * 32) ? 1 : 0;
+      // SM-local variant (k_rollout_sm, plain rollout shape only -- launch_env decides): one block per
+      // SM owning W / SMs env-warps; 3 worker warps per scheduler unless the SM owns fewer env-warps.
+      // CHAOS_B200_SM=0 keeps the global queue; CHAOS_B200_SM_WORKERS / _SM_CHUNK override (tuning).
+      {
+        const char* ov = getenv("CHAOS_B200_SM");
+        if (!(ov && ov[0] == '0') && p.dyn_tma) {
+          const int grid = (int)(W < ctx->sm_count ? W : ctx->sm_count);
+          const int cmax = (int)((W + grid - 1) / grid);
+          int workers = 4 * ((cmax + 3) / 4);
+          workers = workers > 12 ? 12 : workers;
+          if (const char* w = getenv("CHAOS_B200_SM_WORKERS")) { const int k = atoi(w); if (k >= 1 && k <= 16) workers = k; }
+          int sc = 4;
+          if (const char* w = getenv("CHAOS_B200_SM_CHUNK")) { const int k = atoi(w); if (k >= 1 && k <= 16) sc = k; }
+          if (cmax <= 64) { p.sm_grid = grid; p.sm_workers = workers; p.sm_chunk = sc; }
+        }
+      }
       mode = cl::MODE_ROLLOUT_DYN;
       ctx->dyn_launches += 1;
     }
@@ -396,6 +416,7 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
 
 extern "C" int64_t cl_dyn_launch_count(const cl_ctx* ctx) { return ctx ? ctx->dyn_launches : 0; }
 extern "C" int64_t cl_plain_launch_count(const cl_ctx* ctx) { return ctx ? ctx->plain_launches : 0; }
+extern "C" int64_t cl_sm_launch_count(const cl_ctx* ctx) { return ctx ? ctx->sm_launches : 0; }
 
 extern "C" int cl_derivatives(cl_ctx* ctx, void* stream, const void* state, const float* action,
                               void* out, int64_t n) {

@@ -16,6 +16,7 @@ template <typename R>
 struct LorenzPar { R sigma, rho, beta; };
 
 // f(s) + u : dx = sigma (y - x) + u1 ; dy = x (rho - z) - y + u2 ; dz = x y - beta z + u3
+// (textbook form: used for the observation's derivative half, once per control interval)
 template <typename R>
 __device__ __forceinline__ void lorenz_rhs_u(const LorenzPar<R>& q, R x, R y, R z, R u1, R u2, R u3,
                                              R& dx, R& dy, R& dz) {
@@ -24,60 +25,77 @@ __device__ __forceinline__ void lorenz_rhs_u(const LorenzPar<R>& q, R x, R y, R 
   dz = fma(x, y, fma(-q.beta, z, u3));
 }
 
+// The integrator works on the shifted coordinate zs = z - rho for the whole control interval:
+//   dx = sigma (y - x) + u1 ;  dy = -x zs + (u2 - y) ;  d(zs) = x y - beta zs + c3 ,  c3 = u3 - beta rho
+// (u is held over the interval, so c3 is an interval constant).  Same vector field, one FP64
+// instruction less per evaluation: 6 (2 DADD + 4 DFMA) instead of 7, i.e. 45 instead of 49 per RK4
+// substep (24 RHS + 9 stage + 12 combine).  The algorithmic count stays 87 flop.
+template <typename R>
+__device__ __forceinline__ void lorenz_rhs_s(const R sigma, const R beta, R x, R y, R zs, R u1, R u2, R c3,
+                                             R& dx, R& dy, R& dz) {
+  dx = fma(sigma, y - x, u1);
+  dy = fma(-x, zs, u2 - y);
+  dz = fma(x, y, fma(-beta, zs, c3));
+}
+
 // Step sizes (h, h/2, h/3, h/6) and -- on the warp-uniform fast path -- the parameters arrive
 // as kernel-parameter (constant-bank) operands: on sm_100 a DFMA with three distinct register
 // sources issues every 3 cycles per scheduler, one with <= 2 register sources every 2
 // (tools/dfma_probe.cu, DESIGN.md "FP64 cost model"), so only the 8 inherently three-register
 // FMAs per substep (dy, dz of each stage) pay the slow rate.
-template <typename R>
-__device__ __forceinline__ void lorenz_rk4(const LorenzPar<R>& q, R& x, R& y, R& z, R u1, R u2, R u3,
-                                           const R h, const R hh, const R h3, const R h6, int substeps) {
-#pragma unroll 2
-  for (int k = 0; k < substeps; ++k) {
-    R k1x, k1y, k1z, kx, ky, kz, ax, ay, az;
-    lorenz_rhs_u(q, x, y, z, u1, u2, u3, k1x, k1y, k1z);
-    ax = fma(h6, k1x, x); ay = fma(h6, k1y, y); az = fma(h6, k1z, z);
-    lorenz_rhs_u(q, fma(hh, k1x, x), fma(hh, k1y, y), fma(hh, k1z, z), u1, u2, u3, kx, ky, kz);
-    ax = fma(h3, kx, ax); ay = fma(h3, ky, ay); az = fma(h3, kz, az);
-    lorenz_rhs_u(q, fma(hh, kx, x), fma(hh, ky, y), fma(hh, kz, z), u1, u2, u3, k1x, k1y, k1z);
-    ax = fma(h3, k1x, ax); ay = fma(h3, k1y, ay); az = fma(h3, k1z, az);
-    lorenz_rhs_u(q, fma(h, k1x, x), fma(h, k1y, y), fma(h, k1z, z), u1, u2, u3, kx, ky, kz);
-    x = fma(h6, kx, ax); y = fma(h6, ky, ay); z = fma(h6, kz, az);
+#define CL_LORENZ_RK4_SUBSTEP()                                                                     \
+  {                                                                                                 \
+    R k1x, k1y, k1z, kx, ky, kz, ax, ay, az;                                                        \
+    lorenz_rhs_s(sigma, beta, x, y, zs, u1, u2, c3, k1x, k1y, k1z);                                 \
+    ax = fma(h6, k1x, x); ay = fma(h6, k1y, y); az = fma(h6, k1z, zs);                              \
+    lorenz_rhs_s(sigma, beta, fma(hh, k1x, x), fma(hh, k1y, y), fma(hh, k1z, zs), u1, u2, c3, kx, ky, kz);   \
+    ax = fma(h3, kx, ax); ay = fma(h3, ky, ay); az = fma(h3, kz, az);                               \
+    lorenz_rhs_s(sigma, beta, fma(hh, kx, x), fma(hh, ky, y), fma(hh, kz, zs), u1, u2, c3, k1x, k1y, k1z);   \
+    ax = fma(h3, k1x, ax); ay = fma(h3, k1y, ay); az = fma(h3, k1z, az);                            \
+    lorenz_rhs_s(sigma, beta, fma(h, k1x, x), fma(h, k1y, y), fma(h, k1z, zs), u1, u2, c3, kx, ky, kz);      \
+    x = fma(h6, kx, ax); y = fma(h6, ky, ay); zs = fma(h6, kz, az);                                 \
   }
+
+// `br` = beta * rho rounded once (host-side product on the constant path, __dmul_rn on the
+// per-env path: the same IEEE operation, so both paths give identical bits for equal parameters).
+template <typename R>
+__device__ __forceinline__ void lorenz_rk4(const R sigma, const R rho, const R beta, const R br, R& x, R& y, R& z,
+                                           R u1, R u2, R u3, const R h, const R hh, const R h3, const R h6,
+                                           int substeps) {
+  R zs = z - rho;
+  const R c3 = u3 - br;
+#pragma unroll 2
+  for (int k = 0; k < substeps; ++k) CL_LORENZ_RK4_SUBSTEP()
+  z = zs + rho;
 }
 
 // Fully unrolled variant for the common substep counts: without an inner loop ptxas does not
 // force the warp to drain its outstanding loads (the next interval's action prefetch) at a loop
-// head, so that latency hides behind the S x 49 FMA-pipe instructions of the interval.
+// head, so that latency hides behind the S x 45 FMA-pipe instructions of the interval.
 template <typename R, int S>
-__device__ __forceinline__ void lorenz_rk4_fixed(const LorenzPar<R>& q, R& x, R& y, R& z, R u1, R u2, R u3,
-                                                 const R h, const R hh, const R h3, const R h6) {
+__device__ __forceinline__ void lorenz_rk4_fixed(const R sigma, const R rho, const R beta, const R br, R& x, R& y,
+                                                 R& z, R u1, R u2, R u3, const R h, const R hh, const R h3,
+                                                 const R h6) {
+  R zs = z - rho;
+  const R c3 = u3 - br;
 #pragma unroll
-  for (int k = 0; k < S; ++k) {
-    R k1x, k1y, k1z, kx, ky, kz, ax, ay, az;
-    lorenz_rhs_u(q, x, y, z, u1, u2, u3, k1x, k1y, k1z);
-    ax = fma(h6, k1x, x); ay = fma(h6, k1y, y); az = fma(h6, k1z, z);
-    lorenz_rhs_u(q, fma(hh, k1x, x), fma(hh, k1y, y), fma(hh, k1z, z), u1, u2, u3, kx, ky, kz);
-    ax = fma(h3, kx, ax); ay = fma(h3, ky, ay); az = fma(h3, kz, az);
-    lorenz_rhs_u(q, fma(hh, kx, x), fma(hh, ky, y), fma(hh, kz, z), u1, u2, u3, k1x, k1y, k1z);
-    ax = fma(h3, k1x, ax); ay = fma(h3, k1y, ay); az = fma(h3, k1z, az);
-    lorenz_rhs_u(q, fma(h, k1x, x), fma(h, k1y, y), fma(h, k1z, z), u1, u2, u3, kx, ky, kz);
-    x = fma(h6, kx, ax); y = fma(h6, ky, ay); z = fma(h6, kz, az);
-  }
+  for (int k = 0; k < S; ++k) CL_LORENZ_RK4_SUBSTEP()
+  z = zs + rho;
 }
 
 template <typename R>
-__device__ __forceinline__ void lorenz_rk4_any(const LorenzPar<R>& q, R& x, R& y, R& z, R u1, R u2, R u3,
-                                               const R h, const R hh, const R h3, const R h6, int S) {
+__device__ __forceinline__ void lorenz_rk4_any(const R sigma, const R rho, const R beta, const R br, R& x, R& y,
+                                               R& z, R u1, R u2, R u3, const R h, const R hh, const R h3,
+                                               const R h6, int S) {
   if (S == 16) {  // the benchmark configuration: a plain compare-and-branch instead of the jump table
-    lorenz_rk4_fixed<R, 16>(q, x, y, z, u1, u2, u3, h, hh, h3, h6);
+    lorenz_rk4_fixed<R, 16>(sigma, rho, beta, br, x, y, z, u1, u2, u3, h, hh, h3, h6);
     return;
   }
   switch (S) {  // warp-uniform
-    case 8: lorenz_rk4_fixed<R, 8>(q, x, y, z, u1, u2, u3, h, hh, h3, h6); break;
-    case 4: lorenz_rk4_fixed<R, 4>(q, x, y, z, u1, u2, u3, h, hh, h3, h6); break;
-    case 1: lorenz_rk4_fixed<R, 1>(q, x, y, z, u1, u2, u3, h, hh, h3, h6); break;
-    default: lorenz_rk4<R>(q, x, y, z, u1, u2, u3, h, hh, h3, h6, S); break;
+    case 8: lorenz_rk4_fixed<R, 8>(sigma, rho, beta, br, x, y, z, u1, u2, u3, h, hh, h3, h6); break;
+    case 4: lorenz_rk4_fixed<R, 4>(sigma, rho, beta, br, x, y, z, u1, u2, u3, h, hh, h3, h6); break;
+    case 1: lorenz_rk4_fixed<R, 1>(sigma, rho, beta, br, x, y, z, u1, u2, u3, h, hh, h3, h6); break;
+    default: lorenz_rk4<R>(sigma, rho, beta, br, x, y, z, u1, u2, u3, h, hh, h3, h6, S); break;
   }
 }
 
@@ -102,6 +120,14 @@ struct EnvLorenzRK4 {
   __device__ static void store(const S& s, const KParams& p, int64_t i) {
     stp<R>(p, 0, i, s.x); stp<R>(p, 1, i, s.y); stp<R>(p, 2, i, s.z);
     stp<R>(p, 3, i, s.q.sigma); stp<R>(p, 4, i, s.q.rho); stp<R>(p, 5, i, s.q.beta);
+  }
+  // shared-memory planes [NSTATE][32] of one env-warp (k_rollout_sm)
+  __device__ static void load_sm(S& s, const R* b, unsigned lane) {
+    s.x = b[lane]; s.y = b[32 + lane]; s.z = b[64 + lane];
+    s.q.sigma = b[96 + lane]; s.q.rho = b[128 + lane]; s.q.beta = b[160 + lane];
+  }
+  __device__ static void store_sm(const S& s, R* b, unsigned lane) {
+    b[lane] = s.x; b[32 + lane] = s.y; b[64 + lane] = s.z;   // the parameter planes never change
   }
   __device__ static bool uses_noise(const KParams&) { return false; }
   __device__ static bool finite(const S& s) { return isfinite(s.x + s.y + s.z); }
@@ -140,11 +166,11 @@ struct EnvLorenzRK4 {
     const R u2 = mul_keep((R)clipf(a[1], -lim, lim), g);
     const R u3 = mul_keep((R)clipf(a[2], -lim, lim), g);
     if (sizeof(R) == 8) {
-      const LorenzPar<R> qc = {(R)p.nom[0], (R)p.nom[1], (R)p.nom[2]};
-      lorenz_rk4_fixed<R, 16>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6);
+      lorenz_rk4_fixed<R, 16>((R)p.nom[0], (R)p.nom[1], (R)p.nom[2], (R)p.nom_br, s.x, s.y, s.z, u1, u2, u3,
+                              (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6);
     } else {
-      const LorenzPar<R> qc = {(R)p.nomf[0], (R)p.nomf[1], (R)p.nomf[2]};
-      lorenz_rk4_fixed<R, 16>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f);
+      lorenz_rk4_fixed<R, 16>((R)p.nomf[0], (R)p.nomf[1], (R)p.nomf[2], (R)p.nom_brf, s.x, s.y, s.z, u1, u2, u3,
+                              (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f);
     }
     // with the env's own (register) parameters: f(s) + 0 with CONSTANT parameters would need two
     // non-register operands in one DFMA, which forces the constants into registers -- and ptxas
@@ -161,20 +187,21 @@ struct EnvLorenzRK4 {
     const R u1 = mul_keep((R)clipf(a[0], -lim, lim), g);
     const R u2 = mul_keep((R)clipf(a[1], -lim, lim), g);
     const R u3 = mul_keep((R)clipf(a[2], -lim, lim), g);
-    if (sizeof(R) == 8) {
-      if (s.uni) {
-        const LorenzPar<R> qc = {(R)p.nom[0], (R)p.nom[1], (R)p.nom[2]};
-        lorenz_rk4_any<R>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6, p.substeps);
-      } else {
-        lorenz_rk4<R>(s.q, s.x, s.y, s.z, u1, u2, u3, (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6, p.substeps);
-      }
+    if (s.uni) {
+      if (sizeof(R) == 8)
+        lorenz_rk4_any<R>((R)p.nom[0], (R)p.nom[1], (R)p.nom[2], (R)p.nom_br, s.x, s.y, s.z, u1, u2, u3,
+                          (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6, p.substeps);
+      else
+        lorenz_rk4_any<R>((R)p.nomf[0], (R)p.nomf[1], (R)p.nomf[2], (R)p.nom_brf, s.x, s.y, s.z, u1, u2, u3,
+                          (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f, p.substeps);
     } else {
-      if (s.uni) {
-        const LorenzPar<R> qc = {(R)p.nomf[0], (R)p.nomf[1], (R)p.nomf[2]};
-        lorenz_rk4_any<R>(qc, s.x, s.y, s.z, u1, u2, u3, (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f, p.substeps);
-      } else {
-        lorenz_rk4<R>(s.q, s.x, s.y, s.z, u1, u2, u3, (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f, p.substeps);
-      }
+      const R br = mul_rn(s.q.beta, s.q.rho);
+      if (sizeof(R) == 8)
+        lorenz_rk4_any<R>(s.q.sigma, s.q.rho, s.q.beta, br, s.x, s.y, s.z, u1, u2, u3,
+                          (R)p.h, (R)p.hh, (R)p.h3, (R)p.h6, p.substeps);
+      else
+        lorenz_rk4_any<R>(s.q.sigma, s.q.rho, s.q.beta, br, s.x, s.y, s.z, u1, u2, u3,
+                          (R)p.hf, (R)p.hhf, (R)p.h3f, (R)p.h6f, p.substeps);
     }
     observe(s, obs);
     const R e = fabs(s.x) + fabs(s.y) + fabs(s.z);
@@ -196,24 +223,37 @@ __device__ __forceinline__ void pmsm_rhs_u(const PMSMPar& q, const double* x, do
   d[2] = q.sigma * (x[1] - x[2]);
 }
 
-__device__ __forceinline__ void pmsm_rk4(const PMSMPar& q, double* x, double u1, double u2, const double h,
-                                         const double hh, const double h3, const double h6, int substeps) {
+// The integrator works on the shifted coordinate x0s = x0 - gamma for the whole control interval
+// (same idea as lorenz_rhs_s): d0 = x1 x2 + (c1 - x0s), c1 = u1 - gamma ; d1 = -x0s x2 + (u2 - x1) ;
+// d2 = sigma (x1 - x2): 6 FP64 instructions per evaluation instead of 7, 45 instead of 49 per substep.
+__device__ __forceinline__ void pmsm_rhs_s(const double sigma, const double* x, double c1, double u2, double* d) {
+  d[0] = fma(x[1], x[2], c1 - x[0]);
+  d[1] = fma(-x[0], x[2], u2 - x[1]);
+  d[2] = sigma * (x[1] - x[2]);
+}
+
+__device__ __forceinline__ void pmsm_rk4(const double sigma, const double gamma, double* xs, double u1, double u2,
+                                         const double h, const double hh, const double h3, const double h6,
+                                         int substeps) {
+  double x[3] = {xs[0] - gamma, xs[1], xs[2]};
+  const double c1 = u1 - gamma;
 #pragma unroll 2
   for (int k = 0; k < substeps; ++k) {
     double k1[3], k2[3], w[3], acc[3];
-    pmsm_rhs_u(q, x, u1, u2, k1);
+    pmsm_rhs_s(sigma, x, c1, u2, k1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) { acc[c] = fma(h6, k1[c], x[c]); w[c] = fma(hh, k1[c], x[c]); }
-    pmsm_rhs_u(q, w, u1, u2, k2);
+    pmsm_rhs_s(sigma, w, c1, u2, k2);
 #pragma unroll
     for (int c = 0; c < 3; ++c) { acc[c] = fma(h3, k2[c], acc[c]); w[c] = fma(hh, k2[c], x[c]); }
-    pmsm_rhs_u(q, w, u1, u2, k1);
+    pmsm_rhs_s(sigma, w, c1, u2, k1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) { acc[c] = fma(h3, k1[c], acc[c]); w[c] = fma(h, k1[c], x[c]); }
-    pmsm_rhs_u(q, w, u1, u2, k2);
+    pmsm_rhs_s(sigma, w, c1, u2, k2);
 #pragma unroll
     for (int c = 0; c < 3; ++c) x[c] = fma(h6, k2[c], acc[c]);
   }
+  xs[0] = x[0] + gamma; xs[1] = x[1]; xs[2] = x[2];
 }
 
 struct EnvPMSMRK4 {
@@ -233,6 +273,15 @@ struct EnvPMSMRK4 {
 #pragma unroll
     for (int c = 0; c < 3; ++c) { stp<double>(p, c, i, s.a[c]); stp<double>(p, 3 + c, i, s.b[c]); }
     stp<double>(p, 6, i, s.q.sigma); stp<double>(p, 7, i, s.q.gamma);
+  }
+  __device__ static void load_sm(S& s, const double* b, unsigned lane) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { s.a[c] = b[c * 32 + lane]; s.b[c] = b[(3 + c) * 32 + lane]; }
+    s.q.sigma = b[6 * 32 + lane]; s.q.gamma = b[7 * 32 + lane];
+  }
+  __device__ static void store_sm(const S& s, double* b, unsigned lane) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { b[c * 32 + lane] = s.a[c]; b[(3 + c) * 32 + lane] = s.b[c]; }
   }
   __device__ static bool uses_noise(const KParams&) { return false; }
   __device__ static bool finite(const S& s) {
@@ -272,9 +321,8 @@ struct EnvPMSMRK4 {
     const float lim = (float)p.act_limit;
     const double u1 = mul_keep((double)clipf(a[0], -lim, lim), p.act_gain);
     const double u2 = mul_keep((double)clipf(a[1], -lim, lim), p.act_gain);
-    const PMSMPar qc = {p.nom[0], p.nom[1]};
-    pmsm_rk4(qc, s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
-    pmsm_rk4(qc, s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
+    pmsm_rk4(p.nom[0], p.nom[1], s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
+    pmsm_rk4(p.nom[0], p.nom[1], s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
     finish(s, p, obs, rew, term);
   }
   __device__ static void finish(const S& s, const KParams& p, double* obs, double& rew, bool& term) {
@@ -291,12 +339,11 @@ struct EnvPMSMRK4 {
     const double u1 = mul_keep((double)clipf(a[0], -lim, lim), p.act_gain);
     const double u2 = mul_keep((double)clipf(a[1], -lim, lim), p.act_gain);
     if (s.uni) {
-      const PMSMPar qc = {p.nom[0], p.nom[1]};
-      pmsm_rk4(qc, s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
-      pmsm_rk4(qc, s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
+      pmsm_rk4(p.nom[0], p.nom[1], s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
+      pmsm_rk4(p.nom[0], p.nom[1], s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
     } else {
-      pmsm_rk4(s.q, s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
-      pmsm_rk4(s.q, s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
+      pmsm_rk4(s.q.sigma, s.q.gamma, s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
+      pmsm_rk4(s.q.sigma, s.q.gamma, s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
     }
     finish(s, p, obs, rew, term);
   }
@@ -305,5 +352,8 @@ struct EnvPMSMRK4 {
 template <> struct PlainRollout<EnvLorenzRK4<double>> { enum { value = 1 }; };
 template <> struct PlainRollout<EnvLorenzRK4<float>> { enum { value = 1 }; };   // issue-slot bound: same remedy
 template <> struct PlainRollout<EnvPMSMRK4> { enum { value = 1 }; };
+// not terminated <=> |x|+|y|+|z| <= 1e6, hence |x+y+z| <= 1e6: finite
+template <> struct FiniteUnlessTerm<EnvLorenzRK4<double>> { enum { value = 1 }; };
+template <> struct FiniteUnlessTerm<EnvLorenzRK4<float>> { enum { value = 1 }; };
 
 }  // namespace cl

@@ -58,15 +58,19 @@ struct KParams {
   float hf, hhf, h3f, h6f;
   double nom[3];
   float nomf[3];
+  double nom_br;   // Lorenz: beta * rho, PMSM: unused -- the interval constant of the shifted integrator
+  float nom_brf;
   float act_limit_f, act_gain_f;
   // dynamic rollout scheduling (k_rollout_dyn)
   uint32_t* dyn_counter;
   uint32_t* dyn_progress;
   int32_t dyn_chunk, dyn_nchunks, dyn_nwarps, dyn_tma, dyn_grid;
+  // SM-local rollout scheduling (k_rollout_sm): grid, worker warps per block, control intervals per task
+  int32_t sm_grid, sm_workers, sm_chunk;
   // observations go out as contiguous, 16-byte aligned float32 rows -> warp-transposed vector stores
   int32_t rows_fast;
   int32_t no_plain;  // host-side only: keep the generic instantiation (tests, A/B runs)
-  int32_t* host_plain_out;  // host-side only: launch_env reports which instantiation it launched
+  int32_t* host_plain_out;  // host-side only: launch_env reports which instantiation it launched (bit 0 plain, bit 1 k_rollout_sm)
 };
 
 enum LaunchMode { MODE_STEP = 0, MODE_ROLLOUT = 1, MODE_RESET = 2, MODE_INIT = 3, MODE_ROLLOUT_DYN = 4 };
@@ -101,6 +105,9 @@ __device__ __forceinline__ double mul_keep(double a, double b) { return __dmul_r
 // FP32: a three-register FFMA issues at full rate, so the contraction is a free saving of one
 // instruction per stage there (measured: 45.7 vs 42.3 TFLOP/s at 1 Mi envs) -- leave it to ptxas
 __device__ __forceinline__ float mul_keep(float a, float b) { return a * b; }
+// a product rounded exactly once, in either precision (never contracted)
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 
 __device__ __forceinline__ Stream make_stream(const KParams& p, int64_t i, uint64_t step) {
   const uint64_t gid = (uint64_t)(p.env_id_base + i);
@@ -191,6 +198,16 @@ __device__ __forceinline__ void store_obs_rows_warp(float* __restrict__ sm, floa
   __syncwarp();
 }
 
+// plane accessors
+template <typename real>
+__device__ __forceinline__ real ldp(const KParams& p, int c, int64_t i) {
+  return __ldcg((const real*)p.state + (int64_t)c * p.n_pad + i);  // L1-bypassing: see k_rollout_dyn
+}
+template <typename real>
+__device__ __forceinline__ void stp(const KParams& p, int c, int64_t i, real v) {
+  ((real*)p.state)[(int64_t)c * p.n_pad + i] = v;
+}
+
 // ---- one control interval of one env (shared by the static and the dynamic kernels) ----
 
 // The "plain rollout" I/O shape -- what a synthetic-action benchmark or a device-side collector
@@ -204,6 +221,10 @@ __device__ __forceinline__ void store_obs_rows_warp(float* __restrict__ sm, floa
 // for FP64, -12...17 % for the issue-bound FP32 kind).
 // launch_env() picks the instantiation from the launch parameters; results are identical.
 template <class E> struct PlainRollout { enum { value = 0 }; };
+// Kinds whose termination test bounds the state (e.g. |x|+|y|+|z| <= 1e6): a step that does not
+// terminate leaves a finite state, so the plain rollout loop (auto-reset always on) evaluates
+// E::finite only on the rare terminating step.
+template <class E> struct FiniteUnlessTerm { enum { value = 0 }; };
 template <int N> struct SpecTag { enum { value = N }; };
 
 // ---- deferred outputs of the plain rollout loop -------------------------------------------
@@ -323,9 +344,15 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
   ep_ret += (double)rew;
   const bool trunc = E::time_limit(p, ep_len);
   const bool done = term || trunc;
-  fin = E::finite(s);
-  const bool bad = was_finite && !fin;  // divergence EVENT (a diverged env that is never reset would
-                                        // otherwise cost an atomic every step)
+  bool bad;  // divergence EVENT (a diverged env that is never reset would otherwise cost an atomic every step)
+  if constexpr (PLAIN && FiniteUnlessTerm<E>::value != 0) {
+    fin = true;
+    bad = false;
+    if (term) { fin = E::finite(s); bad = was_finite && !fin; }
+  } else {
+    fin = E::finite(s);
+    bad = was_finite && !fin;
+  }
 
   // warp-aggregated statistics (one set of atomics per warp, only when something ended)
   const bool has_term = !PLAIN && p.term_obs != nullptr;
@@ -524,6 +551,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n}\n"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
@@ -674,6 +710,186 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
   }
 }
 
+
+// ---- the SM-local rollout kernel ----------------------------------------------------------
+// Same idea as k_rollout_dyn (env-warp x interval-chunk tasks pulled by persistent worker warps, so
+// that 2048 env-warps spread evenly over 592 schedulers), but the queue is PER SM: block b (one per
+// SM, 120 KB of shared memory so that no two share an SM) owns a contiguous range of 13-14 env-warps
+// for the whole launch.  Their state, episode counters and staged actions live in shared memory; the
+// task counter and the per-env-warp progress words are shared-memory words.  A task hand-off is a
+// few LDS/STS and a block-scope fence instead of a GPU-scope release/acquire through L2 -- in
+// k_rollout_dyn the acquire's L1 invalidate (CCTL.IVALL), the release's ERRBAR and the cold state
+// loads were ~11 % of all stall samples (profiles/r01f_dyn_ncu_full_metrics.txt) -- so tasks can be
+// short (4 intervals: the last round of tasks is 99.6 % full) and no SM waits for another one.
+// Cost: SMs owning 14 env-warps run 1.2 % longer than the 13.84 average.
+// Actions: per env-warp double buffer in shared memory, filled by bulk async copies (mbarrier
+// completion) issued one whole task ahead by whichever warp runs the preceding chunk.
+// Plain rollout I/O shape only (PlainRollout<E>): launch_env falls back to k_rollout_dyn otherwise.
+
+template <class E>
+struct SmLayout {
+  typedef typename E::real real;
+  size_t act, state, ep_ret, ep_len, mbar, prog, total;
+  __host__ __device__ SmLayout(int cnt, int chunk) {
+    size_t o = 0;
+    act = o;    o += (size_t)cnt * 2 * chunk * E::ACT * 32 * sizeof(float);   // 128 B multiples
+    state = o;  o += (size_t)cnt * E::NSTATE * 32 * sizeof(real);
+    ep_ret = o; o += (size_t)cnt * 32 * sizeof(double);
+    ep_len = o; o += (size_t)cnt * 32 * sizeof(int32_t);
+    mbar = o;   o += (size_t)cnt * 2 * sizeof(uint64_t);
+    prog = o;   o += ((size_t)cnt + 1) * sizeof(uint32_t);                    // progress[cnt], counter
+    total = (o + 127) & ~(size_t)127;
+  }
+};
+
+template <class E>
+#ifndef CL_SM_THREADS
+#define CL_SM_THREADS 512
+#endif
+#ifndef CL_SM_MINB
+#define CL_SM_MINB 0
+#endif
+// (512, no minimum-blocks hint): with this bound ptxas keeps the two x-multiplied DFMAs of every RHS
+// evaluation adjacent, so the second one finds x in the operand reuse cache (2.2 instead of 3 issue
+// cycles); (512, 1) and (384, 1) schedule them apart -- checked on the built library by
+// tests/test_sass.py with tools/sass_mix.py
+__global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const KParams p) {
+  typedef typename E::real real;
+  extern __shared__ __align__(128) unsigned char sm_raw[];
+  const unsigned lane = threadIdx.x & 31u;
+  const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int W = p.dyn_nwarps, G = (int)gridDim.x, b = (int)blockIdx.x;
+  const int qn = W / G, rn = W % G;
+  const int e0 = b * qn + (b < rn ? b : rn);
+  const int cnt = qn + (b < rn ? 1 : 0);
+  const int cmax = qn + (rn ? 1 : 0);
+  const int Tc = p.sm_chunk, nchunks = (p.T + Tc - 1) / Tc;
+  const SmLayout<E> L(cmax, Tc);
+  float* const act = (float*)(sm_raw + L.act);
+  real* const st = (real*)(sm_raw + L.state);
+  double* const s_ret = (double*)(sm_raw + L.ep_ret);
+  int32_t* const s_len = (int32_t*)(sm_raw + L.ep_len);
+  uint64_t* const mbar = (uint64_t*)(sm_raw + L.mbar);
+  volatile uint32_t* const prog = (volatile uint32_t*)(sm_raw + L.prog);
+  uint32_t* const counter = (uint32_t*)(sm_raw + L.prog) + cmax;
+  const int per_buf = Tc * E::ACT * 32;  // floats
+
+  // ---- prologue: barriers, queue words, the block's state planes -> shared memory
+  for (int k = threadIdx.x; k < cnt * 2; k += blockDim.x) mbar_init(&mbar[k], 1);
+  for (int k = threadIdx.x; k <= cmax; k += blockDim.x) ((uint32_t*)(sm_raw + L.prog))[k] = 0u;
+  for (int k = threadIdx.x; k < cnt * 32; k += blockDim.x) {
+    const int le = k >> 5, ln = k & 31;
+    const int64_t i = (int64_t)(e0 + le) * 32 + ln;   // < n_pad: the planes are padded
+#pragma unroll
+    for (int c = 0; c < E::NSTATE; ++c) st[(le * E::NSTATE + c) * 32 + ln] = ldp<real>(p, c, i);
+    s_ret[k] = __ldcg(p.ep_return + i);
+    s_len[k] = __ldcg(p.ep_len + i);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  // stage the actions of chunk c of local env-warp le into its buffer (c & 1): lanes 0..len*ACT-1
+  // issue one 128 B copy each, completion counted on the buffer's mbarrier
+  auto stage = [&](int le, int c) {
+    const int t0 = c * Tc;
+    const int len = min(Tc, p.T - t0);
+    uint64_t* bar = &mbar[le * 2 + (c & 1)];
+    float* dst = act + (size_t)(le * 2 + (c & 1)) * per_buf;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(len * E::ACT * 128));
+    __syncwarp();
+    for (int k = (int)lane; k < len * E::ACT; k += 32) {  // every expected byte must be issued
+      const int tl = k / E::ACT, cc = k % E::ACT;
+      const float* src = p.action + (int64_t)(t0 + tl) * p.act_ts + (int64_t)cc * p.act_cs + (int64_t)(e0 + le) * 32;
+      bulk_g2s(dst + (tl * E::ACT + cc) * 32, src, 128u, bar);
+    }
+  };
+  for (int le = wib; le < cnt; le += nw) stage(le, 0);
+
+  const uint64_t step0 = step_base(p);
+  const uint32_t total = (uint32_t)cnt * (uint32_t)nchunks;
+  unsigned bad_acc = 0u;
+  auto grab = [&]() -> uint32_t {
+    uint32_t q = 0;
+    if (lane == 0) q = atomicAdd(counter, 1u);
+    return __shfl_sync(0xffffffffu, q, 0);
+  };
+  uint32_t q = grab();
+  while (q < total) {
+    const int le = (int)(q % (uint32_t)cnt), c = (int)(q / (uint32_t)cnt);
+    const int t0 = c * Tc;
+    const int len = min(Tc, p.T - t0);
+    const int64_t i = (int64_t)(e0 + le) * 32 + lane;
+    const bool live = i < p.n;
+    if (c > 0) {
+      // chunk c-1 of this env-warp was grabbed `cnt` grabs ago (c-major order) by another warp of
+      // this block: practically always finished.  Shared-memory flag, block-scope ordering.
+      if (lane == 0) {
+        while (prog[le] < (uint32_t)c) __nanosleep(64);
+        __threadfence_block();
+      }
+      __syncwarp();
+    }
+    if (c + 1 < nchunks) {
+      // buffer (c+1)&1 was last read (generic proxy) during chunk c-1, which has been published
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      stage(le, c + 1);
+    }
+    typename E::S s = {};
+    E::load_sm(s, st + (size_t)le * E::NSTATE * 32, lane);
+    int32_t ep_len = s_len[le * 32 + lane];
+    double ep_ret = s_ret[le * 32 + lane];
+    E::prepare(s, p, live);
+    {
+      uint64_t* bar = &mbar[le * 2 + (c & 1)];
+      const uint32_t parity = (uint32_t)(c >> 1) & 1u;
+      while (!mbar_try_wait(bar, parity)) {}
+    }
+    const float* ab = act + (size_t)(le * 2 + (c & 1)) * per_buf;
+    bool fin = E::finite(s);
+    PlainPending<E> pend;
+    pend.begin(p, i, t0);
+    auto intervals = [&](auto spec_tag) {
+      constexpr int SPEC = decltype(spec_tag)::value;
+      for (int tl = 0; tl < len; ++tl) {
+        const int t = t0 + tl;
+        const uint64_t step = step0 + (uint64_t)t;
+        float a[E::ACT];
+#pragma unroll
+        for (int cc = 0; cc < E::ACT; ++cc) a[cc] = ab[(tl * E::ACT + cc) * 32 + lane];
+        env_interval<E, true, true, SPEC, true>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, false, false, true,
+                                                bad_acc, nullptr, fin, &pend);
+      }
+    };
+    if (E::spec(s, p) == 1) intervals(SpecTag<1>{});
+    else intervals(SpecTag<0>{});
+    E::store_sm(s, st + (size_t)le * E::NSTATE * 32, lane);
+    s_len[le * 32 + lane] = ep_len;
+    s_ret[le * 32 + lane] = ep_ret;
+    // publish: the warp barrier orders every lane's shared-memory stores before lane 0's flag store
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      prog[le] = (uint32_t)c + 1u;
+    }
+    if (CL_PLAIN_DEFER) plain_emit<E, true>(p, i, live, pend);   // the last interval's outputs, after the hand-off
+    q = grab();
+  }
+  if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
+
+  // ---- epilogue: state planes and episode counters back to global memory
+  __syncthreads();
+  for (int k = threadIdx.x; k < cnt * 32; k += blockDim.x) {
+    const int le = k >> 5, ln = k & 31;
+    const int64_t i = (int64_t)(e0 + le) * 32 + ln;
+    if (i < p.n) {
+#pragma unroll
+      for (int c = 0; c < E::NSTATE; ++c) stp<real>(p, c, i, st[(le * E::NSTATE + c) * 32 + ln]);
+      p.ep_return[i] = s_ret[k];
+      p.ep_len[i] = s_len[k];
+    }
+  }
+}
+
 template <class E>
 __global__ void __launch_bounds__(256) k_reset(const KParams p) {
   typedef typename E::real real;
@@ -744,6 +960,25 @@ cudaError_t launch_env(const KParams& p_in, int mode, cudaStream_t st, int block
     case MODE_RESET: k_reset<E><<<grid, block, 0, st>>>(p); break;
     case MODE_INIT: k_init<E><<<grid, block, 0, st>>>(p); break;
     case MODE_ROLLOUT_DYN: {
+      if constexpr (HAS_PLAIN) {
+        if (plain && p.sm_grid > 0) {
+          // SM-local scheduling: one block per SM (>= 120 KB of shared memory each keeps two blocks off one SM)
+          const int cmax = (p.dyn_nwarps + p.sm_grid - 1) / p.sm_grid;
+          size_t smem = SmLayout<E>(cmax, p.sm_chunk).total;
+          if (smem < 120 * 1024) smem = 120 * 1024;
+          if (smem <= 200 * 1024) {
+            static bool attr_set = false;
+            if (!attr_set) {
+              cudaError_t e = cudaFuncSetAttribute(k_rollout_sm<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+              if (e != cudaSuccess) return e;
+              attr_set = true;
+            }
+            if (p_in.host_plain_out) *p_in.host_plain_out |= 2;
+            k_rollout_sm<E><<<(unsigned)p.sm_grid, (unsigned)p.sm_workers * 32, smem, st>>>(p);
+            break;
+          }
+        }
+      }
       // block = 128 threads (one warp per scheduler), p.dyn_grid blocks, smem = action staging
       const size_t smem = (size_t)4 * p.dyn_chunk * E::ACT * 32 * sizeof(float) + 4 * sizeof(uint64_t);
       if (plain) k_rollout_dyn<E, HAS_PLAIN><<<(unsigned)p.dyn_grid, 128, smem, st>>>(p);
@@ -771,16 +1006,6 @@ cudaError_t dyn_occupancy(int chunk, int* blocks_per_sm) {
   }
   *blocks_per_sm = occ < occ_plain ? occ : occ_plain;
   return cudaSuccess;
-}
-
-// plane accessors
-template <typename real>
-__device__ __forceinline__ real ldp(const KParams& p, int c, int64_t i) {
-  return __ldcg((const real*)p.state + (int64_t)c * p.n_pad + i);  // L1-bypassing: see k_rollout_dyn
-}
-template <typename real>
-__device__ __forceinline__ void stp(const KParams& p, int c, int64_t i, real v) {
-  ((real*)p.state)[(int64_t)c * p.n_pad + i] = v;
 }
 
 }  // namespace cl

@@ -274,6 +274,9 @@ int64_t cl_dyn_launch_count(const cl_ctx* ctx);
 /* rollouts that ran on the plain-I/O instantiation of the rollout kernels (FP64-bound kinds:
  * float32 SoA observation planes, real-typed reward, done flags, auto-reset, no term_obs) */
 int64_t cl_plain_launch_count(const cl_ctx* ctx);
+/* rollouts that ran on the SM-local kernel (k_rollout_sm: per-SM task queue, env state in shared
+ * memory across the launch) -- the instantiation the bench workload selects at 65,536 envs */
+int64_t cl_sm_launch_count(const cl_ctx* ctx);
 
 /* -- device-side SB3 plumbing that directly follows the env step; all
  *    pointers are DEVICE pointers, calls only enqueue on `stream` of the current device. */

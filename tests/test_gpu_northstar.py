@@ -205,6 +205,112 @@ def test_dynamic_rollout_many_handoffs_stress(kind, monkeypatch):
         b.close()
 
 
+@pytest.mark.parametrize("kind,n,T,workers,chunk", [
+    ("lorenz_rk4", 65536, 37, None, None),    # bench shape, default workers / chunk, short last chunk
+    ("lorenz_rk4", 65536, 64, "16", "1"),     # more workers than an SM has env-warps: the surplus waits
+    ("lorenz_rk4", 40000, 29, "12", "3"),     # ragged: partial last warp, SMs own 8 or 9 env-warps
+    ("lorenz_rk4", 70001, 33, "8", "8"),
+    ("lorenz_rk4_f32", 65536, 26, None, "2"),
+    ("pmsm_rk4", 50000, 21, None, None),
+    ("lorenz_rk4", 3000, 40, None, None),     # fewer env-warps (94) than SMs: one env-warp per block
+])
+def test_sm_local_rollout_is_bit_identical_to_static(kind, n, T, workers, chunk, monkeypatch):
+    """k_rollout_sm (per-SM task queue, env state / episode counters / staged actions in shared memory
+    for the whole launch) must reproduce the static one-thread-per-env kernel bit for bit, with
+    episodes ending (TimeLimit 11) inside the window, and so must the global-queue kernel it replaces."""
+    import torch
+    kw = dict(seed=13, autoreset=True, max_episode_steps=11)
+    res = {}
+    for mode in ("static", "sm", "dyn"):
+        monkeypatch.setenv("CHAOS_B200_DYN", "0" if mode == "static" else "1")
+        monkeypatch.setenv("CHAOS_B200_SM", "0" if mode == "dyn" else "1")
+        for k, v in (("CHAOS_B200_SM_WORKERS", workers), ("CHAOS_B200_SM_CHUNK", chunk)):
+            if v is None:
+                monkeypatch.delenv(k, raising=False)
+            else:
+                monkeypatch.setenv(k, v)
+        b = H.gpu_batch(kind, n, **kw)
+        b.reset()
+        g = torch.Generator(device="cpu").manual_seed(5)
+        soa = ((torch.rand((T, b.act_dim, b.n_pad), generator=g) * 2 - 1) * float(b.layout.act_high)).to(b.device)
+        out = b.rollout(T, soa[:, :, :n].permute(0, 2, 1))
+        torch.cuda.synchronize()
+        assert b.sm_launch_count == (1 if mode == "sm" else 0), mode
+        assert b.dyn_launch_count == (0 if mode == "static" else 1), mode
+        res[mode] = (out["obs"].clone(), out["reward"].clone(), out["done"].clone(), b.state.clone(),
+                     b.ep_len.clone(), b.ep_return.clone(), b.stats())
+        b.close()
+    for other in ("sm", "dyn"):
+        for x, y in zip(res["static"][:6], res[other][:6]):
+            assert torch.equal(torch.nan_to_num(x[..., :n].double()), torch.nan_to_num(y[..., :n].double())), other
+        s0, s1 = res["static"][6], res[other][6]
+        for key in ("episodes", "length_sum", "terminated", "truncated", "nonfinite_events"):
+            assert s0[key] == s1[key], (other, key)
+        assert s0["episodes"] > 0
+        assert np.isclose(s0["return_sum"], s1["return_sum"], rtol=1e-9)
+
+
+def test_sm_local_rollout_repeated_launches_and_jitter(monkeypatch):
+    """Back-to-back launches (state leaves and re-enters shared memory every launch) with per-env
+    parameters (the generic, register-parameter interval loop) against the static kernel."""
+    import torch
+    n, T = 65536, 24
+    ref = None
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CHAOS_B200_DYN", mode)
+        b = H.gpu_batch("lorenz_rk4", n, seed=3, autoreset=True, max_episode_steps=17, param_jitter=0.1)
+        b.reset()
+        g = torch.Generator(device="cpu").manual_seed(2)
+        soa = (torch.rand((T, b.act_dim, b.n_pad), generator=g) * 2 - 1).to(b.device)
+        outs = []
+        for rep in range(3):
+            o = b.rollout(T, soa[:, :, :n].permute(0, 2, 1))
+            outs.append((o["obs"].clone(), o["reward"].clone(), o["done"].clone()))
+        torch.cuda.synchronize()
+        assert b.sm_launch_count == (3 if mode == "1" else 0)
+        cur = (outs, b.state.clone(), b.ep_len.clone(), b.ep_return.clone())
+        if ref is None:
+            ref = cur
+        else:
+            for (a0, a1, a2), (c0, c1, c2) in zip(ref[0], cur[0]):
+                assert torch.equal(a0, c0) and torch.equal(a1, c1) and torch.equal(a2, c2)
+            assert torch.equal(ref[1], cur[1]) and torch.equal(ref[2], cur[2]) and torch.equal(ref[3], cur[3])
+        b.close()
+
+
+def test_bench_configuration_against_the_oracle_directly(oracle_api, monkeypatch):
+    """BASELINE configs[1] on the instantiation bench.py times: Lorenz RK4 x 16, FP64, 65,536 envs,
+    given actions, plain rollout shape -> k_rollout_sm.  State, reward and done flags of a 4,096-env
+    slab (same global env ids) against oracle.rollout, T = 32 control intervals with TimeLimit resets
+    inside the window."""
+    import torch
+    O = oracle_api
+    for k in ("CHAOS_B200_DYN", "CHAOS_B200_SM", "CHAOS_B200_SM_WORKERS", "CHAOS_B200_SM_CHUNK", "CHAOS_B200_PLAIN"):
+        monkeypatch.delenv(k, raising=False)
+    n, T, S = 65536, 32, 16
+    kw = dict(seed=7, autoreset=True, max_episode_steps=20, substeps=S)
+    b = H.gpu_batch("lorenz_rk4", n, **kw)
+    b.reset()
+    g = torch.Generator(device="cpu").manual_seed(11)
+    soa = (torch.rand((T, b.act_dim, b.n_pad), generator=g) * 2 - 1).to(b.device)
+    out = b.rollout(T, soa[:, :, :n].permute(0, 2, 1))
+    torch.cuda.synchronize()
+    assert b.dyn_launch_count == 1 and b.plain_launch_count == 1 and b.sm_launch_count == 1
+    for lo, m in ((0, 2048), (41_000, 4096), (65536 - 1024, 1024)):
+        o = O.Oracle("lorenz_rk4", m, flags=O.F_AUTORESET, seed=7, substeps=S, dt=0.01, act_limit=1.0, act_gain=50.0,
+                     max_episode_steps=20, env_id_base=lo)
+        o.reset()
+        a_np = np.zeros((T, o.act_dim, o.n_pad), np.float32)
+        a_np[:, :, :m] = soa[:, :, lo:lo + m].cpu().numpy()
+        ref = o.rollout(T, a_np)
+        H.assert_close(out["reward"][:, lo:lo + m].cpu().numpy(), ref["reward"][:, :m], 1e-11, "reward vs oracle", atol=1e-11)
+        assert np.array_equal(out["done"][:, lo:lo + m].cpu().numpy(), ref["done"][:, :m])
+        H.assert_close(out["obs"][:, :, lo:lo + m].double().cpu().numpy(), ref["obs"][:, :, :m], 1e-6, "obs (f32)", atol=1e-5)
+        H.assert_close(b.state[:3, lo:lo + m].cpu().numpy(), o.state[:3, :m], 1e-11, "state vs oracle", atol=1e-11)
+        assert np.array_equal(b.ep_len[lo:lo + m].cpu().numpy(), o.ep_len[:m])
+    b.close()
+
+
 def test_pmsm_rk4_with_parameter_jitter_vs_oracle_and_scipy(oracle_api):
     """BASELINE configs[2]: chaotic PMSM pair, 65,536 envs, FP64, per-env sigma/gamma ~ U(0.9,1.1) x
     nominal.  Per control interval vs the oracle (1e-12) and, for a sample, vs DOP853 (1e-9)."""
