@@ -125,9 +125,12 @@ SYMBOLS = [
     ("cl_gae", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_double, C.c_double, C.c_int32, C.c_int64, C.c_int64, _VP, _VP]),
     ("cl_obs_moments", C.c_int, [_VP, _VP, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _VP, _VP]),
     ("cl_rms_update", C.c_int, [_VP, _VP, C.c_int64, C.c_int32, _VP, _VP, _VP]),
+    ("cl_moments_f64", C.c_int, [_VP, _VP, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _VP, _VP]),
     ("cl_obs_normalize", C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                    _VP, _VP, C.c_double, C.c_double]),
     ("cl_frame_stack", C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_int64, _VP, C.c_int64, C.c_int32, C.c_int32]),
+    ("cl_frame_stack_term", C.c_int, [_VP, _VP, _VP, C.c_int64, C.c_int64, _VP, _VP, C.c_int64, C.c_int64, _VP,
+                                      C.c_int64, C.c_int32, C.c_int32]),
     ("cl_eval_metrics", C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32,
                                   C.c_double, C.c_double, _VP]),
     ("cl_philox4x32_10", None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

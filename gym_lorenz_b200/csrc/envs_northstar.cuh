@@ -232,28 +232,58 @@ __device__ __forceinline__ void pmsm_rhs_s(const double sigma, const double* x, 
   d[2] = sigma * (x[1] - x[2]);
 }
 
-__device__ __forceinline__ void pmsm_rk4(const double sigma, const double gamma, double* xs, double u1, double u2,
-                                         const double h, const double hh, const double h3, const double h6,
-                                         int substeps) {
-  double x[3] = {xs[0] - gamma, xs[1], xs[2]};
-  const double c1 = u1 - gamma;
-#pragma unroll 2
-  for (int k = 0; k < substeps; ++k) {
-    double k1[3], k2[3], w[3], acc[3];
-    pmsm_rhs_s(sigma, x, c1, u2, k1);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { acc[c] = fma(h6, k1[c], x[c]); w[c] = fma(hh, k1[c], x[c]); }
-    pmsm_rhs_s(sigma, w, c1, u2, k2);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { acc[c] = fma(h3, k2[c], acc[c]); w[c] = fma(hh, k2[c], x[c]); }
-    pmsm_rhs_s(sigma, w, c1, u2, k1);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { acc[c] = fma(h3, k1[c], acc[c]); w[c] = fma(h, k1[c], x[c]); }
-    pmsm_rhs_s(sigma, w, c1, u2, k2);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) x[c] = fma(h6, k2[c], acc[c]);
+#define CL_PMSM_RK4_SUBSTEP(x, c1, u2)                                                                    \
+  {                                                                                                        \
+    double k1[3], k2[3], w[3], acc[3];                                                                     \
+    pmsm_rhs_s(sigma, x, c1, u2, k1);                                                                      \
+    _Pragma("unroll") for (int c = 0; c < 3; ++c) { acc[c] = fma(h6, k1[c], x[c]); w[c] = fma(hh, k1[c], x[c]); }   \
+    pmsm_rhs_s(sigma, w, c1, u2, k2);                                                                      \
+    _Pragma("unroll") for (int c = 0; c < 3; ++c) { acc[c] = fma(h3, k2[c], acc[c]); w[c] = fma(hh, k2[c], x[c]); } \
+    pmsm_rhs_s(sigma, w, c1, u2, k1);                                                                      \
+    _Pragma("unroll") for (int c = 0; c < 3; ++c) { acc[c] = fma(h3, k1[c], acc[c]); w[c] = fma(h, k1[c], x[c]); }  \
+    pmsm_rhs_s(sigma, w, c1, u2, k2);                                                                      \
+    _Pragma("unroll") for (int c = 0; c < 3; ++c) x[c] = fma(h6, k2[c], acc[c]);                           \
   }
-  xs[0] = x[0] + gamma; xs[1] = x[1]; xs[2] = x[2];
+
+// Master (free-running, a) and slave (controlled, b) advance in the SAME substep loop: two independent
+// dependency chains per thread, so ~3 worker warps per scheduler see twice the instruction-level
+// parallelism.  S > 0: compile-time substep count, fully unrolled (the control interval becomes one
+// straight line of code); S == 0: run-time count.  Either way the operations per system, and hence the
+// bits, are the same.
+template <int S>
+__device__ __forceinline__ void pmsm_rk4_pair(const double sigma, const double gamma, double* a, double* b,
+                                              double u1, double u2, const double h, const double hh, const double h3,
+                                              const double h6, int substeps) {
+  double xa[3] = {a[0] - gamma, a[1], a[2]};
+  double xb[3] = {b[0] - gamma, b[1], b[2]};
+  const double c1a = 0.0 - gamma, c1b = u1 - gamma;
+  if (S > 0) {
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      CL_PMSM_RK4_SUBSTEP(xa, c1a, 0.0)
+      CL_PMSM_RK4_SUBSTEP(xb, c1b, u2)
+    }
+  } else {
+#pragma unroll 2
+    for (int k = 0; k < substeps; ++k) {
+      CL_PMSM_RK4_SUBSTEP(xa, c1a, 0.0)
+      CL_PMSM_RK4_SUBSTEP(xb, c1b, u2)
+    }
+  }
+  a[0] = xa[0] + gamma; a[1] = xa[1]; a[2] = xa[2];
+  b[0] = xb[0] + gamma; b[1] = xb[1]; b[2] = xb[2];
+}
+
+__device__ __forceinline__ void pmsm_rk4_pair_any(const double sigma, const double gamma, double* a, double* b,
+                                                  double u1, double u2, const double h, const double hh,
+                                                  const double h3, const double h6, int S) {
+  switch (S) {  // warp-uniform
+    case 4: pmsm_rk4_pair<4>(sigma, gamma, a, b, u1, u2, h, hh, h3, h6, S); break;   // the env's default
+    case 8: pmsm_rk4_pair<8>(sigma, gamma, a, b, u1, u2, h, hh, h3, h6, S); break;
+    case 2: pmsm_rk4_pair<2>(sigma, gamma, a, b, u1, u2, h, hh, h3, h6, S); break;
+    case 1: pmsm_rk4_pair<1>(sigma, gamma, a, b, u1, u2, h, hh, h3, h6, S); break;
+    default: pmsm_rk4_pair<0>(sigma, gamma, a, b, u1, u2, h, hh, h3, h6, S); break;
+  }
 }
 
 struct EnvPMSMRK4 {
@@ -321,8 +351,7 @@ struct EnvPMSMRK4 {
     const float lim = (float)p.act_limit;
     const double u1 = mul_keep((double)clipf(a[0], -lim, lim), p.act_gain);
     const double u2 = mul_keep((double)clipf(a[1], -lim, lim), p.act_gain);
-    pmsm_rk4(p.nom[0], p.nom[1], s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
-    pmsm_rk4(p.nom[0], p.nom[1], s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
+    pmsm_rk4_pair_any(p.nom[0], p.nom[1], s.a, s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
     finish(s, p, obs, rew, term);
   }
   __device__ static void finish(const S& s, const KParams& p, double* obs, double& rew, bool& term) {
@@ -338,13 +367,8 @@ struct EnvPMSMRK4 {
     const float lim = (float)p.act_limit;
     const double u1 = mul_keep((double)clipf(a[0], -lim, lim), p.act_gain);
     const double u2 = mul_keep((double)clipf(a[1], -lim, lim), p.act_gain);
-    if (s.uni) {
-      pmsm_rk4(p.nom[0], p.nom[1], s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
-      pmsm_rk4(p.nom[0], p.nom[1], s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
-    } else {
-      pmsm_rk4(s.q.sigma, s.q.gamma, s.a, 0.0, 0.0, p.h, p.hh, p.h3, p.h6, p.substeps);
-      pmsm_rk4(s.q.sigma, s.q.gamma, s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
-    }
+    if (s.uni) pmsm_rk4_pair_any(p.nom[0], p.nom[1], s.a, s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
+    else pmsm_rk4_pair_any(s.q.sigma, s.q.gamma, s.a, s.b, u1, u2, p.h, p.hh, p.h3, p.h6, p.substeps);
     finish(s, p, obs, rew, term);
   }
 };
@@ -355,5 +379,9 @@ template <> struct PlainRollout<EnvPMSMRK4> { enum { value = 1 }; };
 // not terminated <=> |x|+|y|+|z| <= 1e6, hence |x+y+z| <= 1e6: finite
 template <> struct FiniteUnlessTerm<EnvLorenzRK4<double>> { enum { value = 1 }; };
 template <> struct FiniteUnlessTerm<EnvLorenzRK4<float>> { enum { value = 1 }; };
+// not terminated <=> sum |a_c - b_c| <= 1000: every difference is finite, hence every a_c, b_c (inf - x is
+// inf or NaN).  The six finite values could only overflow `finite`'s sum above ~3e307 -- a magnitude at
+// which the quadratic right-hand side overflows inside the same step, so it is never reached.
+template <> struct FiniteUnlessTerm<EnvPMSMRK4> { enum { value = 1 }; };
 
 }  // namespace cl

@@ -551,6 +551,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -736,8 +739,8 @@ struct SmLayout {
     state = o;  o += (size_t)cnt * E::NSTATE * 32 * sizeof(real);
     ep_ret = o; o += (size_t)cnt * 32 * sizeof(double);
     ep_len = o; o += (size_t)cnt * 32 * sizeof(int32_t);
-    mbar = o;   o += (size_t)cnt * 2 * sizeof(uint64_t);
-    prog = o;   o += ((size_t)cnt + 1) * sizeof(uint32_t);                    // progress[cnt], counter
+    mbar = o;   o += (size_t)cnt * 3 * sizeof(uint64_t);                      // 2 action buffers + hand-off
+    prog = o;   o += sizeof(uint32_t);                                        // task counter
     total = (o + 127) & ~(size_t)127;
   }
 };
@@ -763,20 +766,26 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   const int e0 = b * qn + (b < rn ? b : rn);
   const int cnt = qn + (b < rn ? 1 : 0);
   const int cmax = qn + (rn ? 1 : 0);
-  const int Tc = p.sm_chunk, nchunks = (p.T + Tc - 1) / Tc;
+  // Task schedule of one env-warp: full chunks of Tc control intervals, then -- so that the last round
+  // of tasks, in which workers run dry, is short -- the final two chunks' worth in pieces of Tc / 4.
+  const int Tc = p.sm_chunk, Ts = Tc >= 4 ? Tc / 4 : 1;
+  const int n_full = p.T > 2 * Tc ? (p.T - 2 * Tc) / Tc : 0;
+  const int t_tail = n_full * Tc;
+  const int nchunks = n_full + (p.T - t_tail + Ts - 1) / Ts;
+  auto chunk_t0 = [&](int c) { return c < n_full ? c * Tc : t_tail + (c - n_full) * Ts; };
+  auto chunk_len = [&](int c) { return c < n_full ? Tc : min(Ts, p.T - (t_tail + (c - n_full) * Ts)); };
   const SmLayout<E> L(cmax, Tc);
   float* const act = (float*)(sm_raw + L.act);
   real* const st = (real*)(sm_raw + L.state);
   double* const s_ret = (double*)(sm_raw + L.ep_ret);
   int32_t* const s_len = (int32_t*)(sm_raw + L.ep_len);
-  uint64_t* const mbar = (uint64_t*)(sm_raw + L.mbar);
-  volatile uint32_t* const prog = (volatile uint32_t*)(sm_raw + L.prog);
-  uint32_t* const counter = (uint32_t*)(sm_raw + L.prog) + cmax;
+  uint64_t* const mbar = (uint64_t*)(sm_raw + L.mbar);     // [le][0..1]: action buffers, [le][2]: hand-off
+  uint32_t* const counter = (uint32_t*)(sm_raw + L.prog);
   const int per_buf = Tc * E::ACT * 32;  // floats
 
-  // ---- prologue: barriers, queue words, the block's state planes -> shared memory
-  for (int k = threadIdx.x; k < cnt * 2; k += blockDim.x) mbar_init(&mbar[k], 1);
-  for (int k = threadIdx.x; k <= cmax; k += blockDim.x) ((uint32_t*)(sm_raw + L.prog))[k] = 0u;
+  // ---- prologue: barriers, queue word, the block's state planes -> shared memory
+  for (int k = threadIdx.x; k < cnt * 3; k += blockDim.x) mbar_init(&mbar[k], 1);
+  if (threadIdx.x == 0) *counter = 0u;
   for (int k = threadIdx.x; k < cnt * 32; k += blockDim.x) {
     const int le = k >> 5, ln = k & 31;
     const int64_t i = (int64_t)(e0 + le) * 32 + ln;   // < n_pad: the planes are padded
@@ -791,9 +800,9 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   // stage the actions of chunk c of local env-warp le into its buffer (c & 1): lanes 0..len*ACT-1
   // issue one 128 B copy each, completion counted on the buffer's mbarrier
   auto stage = [&](int le, int c) {
-    const int t0 = c * Tc;
-    const int len = min(Tc, p.T - t0);
-    uint64_t* bar = &mbar[le * 2 + (c & 1)];
+    const int t0 = chunk_t0(c);
+    const int len = chunk_len(c);
+    uint64_t* bar = &mbar[le * 3 + (c & 1)];
     float* dst = act + (size_t)(le * 2 + (c & 1)) * per_buf;
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)(len * E::ACT * 128));
     __syncwarp();
@@ -816,22 +825,26 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   uint32_t q = grab();
   while (q < total) {
     const int le = (int)(q % (uint32_t)cnt), c = (int)(q / (uint32_t)cnt);
-    const int t0 = c * Tc;
-    const int len = min(Tc, p.T - t0);
+    const int t0 = chunk_t0(c);
+    const int len = chunk_len(c);
     const int64_t i = (int64_t)(e0 + le) * 32 + lane;
     const bool live = i < p.n;
     if (c > 0) {
-      // chunk c-1 of this env-warp was grabbed `cnt` grabs ago (c-major order) by another warp of
-      // this block: practically always finished.  Shared-memory flag, block-scope ordering.
-      if (lane == 0) {
-        while (prog[le] < (uint32_t)c) __nanosleep(64);
-        __threadfence_block();
-      }
-      __syncwarp();
+      // Hand-off: chunk c-1 of this env-warp was grabbed `cnt` grabs ago (c-major order) by another
+      // warp of this block and has practically always finished.  Its completion is phase c-1 of the
+      // env-warp's hand-off mbarrier (arrive = release, try_wait = acquire, both CTA scope): no
+      // MEMBAR -- a __threadfence_block() here also waits for the warp's outstanding global output
+      // stores, ~0.5 us per task.
+      uint64_t* hb = &mbar[le * 3 + 2];
+      const uint32_t parity = (uint32_t)(c - 1) & 1u;
+      while (!mbar_try_wait(hb, parity)) __nanosleep(32);
     }
     if (c + 1 < nchunks) {
-      // buffer (c+1)&1 was last read (generic proxy) during chunk c-1, which has been published
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      // Buffer (c+1)&1 was last READ (LDS, generic proxy) during chunk c-1; those loads had returned
+      // their values before that chunk's warp arrived on the hand-off barrier we just waited on, so
+      // the bulk copy (async proxy) cannot overtake them.  No fence.proxy.async here -- it compiles to
+      // MEMBAR.ALL.CTA, which also waits for this warp's outstanding global output stores; the
+      // write-after-read direction is ordered by the mbarrier alone (the usual TMA pipeline pattern).
       stage(le, c + 1);
     }
     typename E::S s = {};
@@ -840,7 +853,7 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
     double ep_ret = s_ret[le * 32 + lane];
     E::prepare(s, p, live);
     {
-      uint64_t* bar = &mbar[le * 2 + (c & 1)];
+      uint64_t* bar = &mbar[le * 3 + (c & 1)];
       const uint32_t parity = (uint32_t)(c >> 1) & 1u;
       while (!mbar_try_wait(bar, parity)) {}
     }
@@ -865,12 +878,9 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
     E::store_sm(s, st + (size_t)le * E::NSTATE * 32, lane);
     s_len[le * 32 + lane] = ep_len;
     s_ret[le * 32 + lane] = ep_ret;
-    // publish: the warp barrier orders every lane's shared-memory stores before lane 0's flag store
+    // publish: the warp barrier orders every lane's shared-memory stores before lane 0's arrive
     __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      prog[le] = (uint32_t)c + 1u;
-    }
+    if (lane == 0) mbar_arrive(&mbar[le * 3 + 2]);
     if (CL_PLAIN_DEFER) plain_emit<E, true>(p, i, live, pend);   // the last interval's outputs, after the hand-off
     q = grab();
   }

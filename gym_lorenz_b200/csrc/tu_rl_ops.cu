@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(256) k_gae(const float* __restrict__ rew, cons
 }
 
 // ---- running moments: per-feature sum(x - shift) and sum((x - shift)^2) over envs --------
-template <int MAXD>
-__global__ void __launch_bounds__(256) k_moments(const float* __restrict__ obs, int64_t es, int64_t cs, int64_t n,
+template <int MAXD, typename TIN>
+__global__ void __launch_bounds__(256) k_moments(const TIN* __restrict__ obs, int64_t es, int64_t cs, int64_t n,
                                                  int dim, const double* __restrict__ shift, double* __restrict__ out) {
   double s1[MAXD], s2[MAXD];
 #pragma unroll
@@ -80,28 +80,122 @@ __global__ void __launch_bounds__(256) k_moments(const float* __restrict__ obs, 
 }
 
 // ---- normalise + clip: clip((x - mean) / sqrt(var + eps), -clip, clip).astype(float32) ----
+// ROWS: the output is a contiguous, 16-byte aligned [N][dim] block (what a policy network reads): a
+// warp's 32 rows are one run of 32*dim floats, written as whole float4 vectors through a shared-memory
+// transpose instead of `dim` stores of 32 scattered 4-byte words each.
+template <bool ROWS>
 __global__ void __launch_bounds__(256) k_normalize(const float* __restrict__ in, int64_t ies, int64_t ics,
                                                    float* __restrict__ out, int64_t oes, int64_t ocs, int64_t n,
                                                    int dim, const double* __restrict__ mean,
                                                    const double* __restrict__ var, double eps, double clip) {
+  extern __shared__ __align__(16) float sm_norm[];   // ROWS: [warps][32 * dim]
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  for (int c = 0; c < dim; ++c) {
-    double z = ((double)in[i * ies + c * ics] - mean[c]) / sqrt(var[c] + eps);
-    z = z < -clip ? -clip : (z > clip ? clip : z);
-    out[i * oes + c * ocs] = (float)z;
+  const unsigned lane = threadIdx.x & 31u;
+  float* sm = sm_norm + (threadIdx.x >> 5) * (32 * dim);
+  if (i < n) {
+    for (int c = 0; c < dim; ++c) {
+      double z = ((double)in[i * ies + c * ics] - mean[c]) / sqrt(var[c] + eps);
+      z = z < -clip ? -clip : (z > clip ? clip : z);
+      if (ROWS) sm[lane * dim + c] = (float)z;
+      else out[i * oes + c * ocs] = (float)z;
+    }
+  }
+  if (ROWS) {
+    __syncwarp();
+    const int64_t row0 = i - (int64_t)lane;
+    const int64_t rows = n - row0;
+    const int nflt = (int)(rows >= 32 ? 32 : (rows > 0 ? rows : 0)) * dim;
+    float* dst = out + row0 * dim;
+    for (int k = (int)lane * 4; k + 3 < nflt; k += 128)
+      *reinterpret_cast<float4*>(dst + k) = *reinterpret_cast<const float4*>(sm + k);
+    for (int k = (nflt & ~3) + (int)lane; k < nflt; k += 32) dst[k] = sm[k];
   }
 }
 
 // ---- frame stack (SB3 StackedObservations, 1-D observations stacked along the last axis) --
 // stacked[i] = roll(stacked[i], -dim); if done[i]: stacked[i] = 0; stacked[i, -dim:] = obs[i]
+// and, for envs that finished an episode (StackedObservations.update): the stacked terminal
+// observation term_out[i] = concat(rolled previous stack minus its last frame, term_in[i]).
+//
+// One warp owns 32 consecutive rows = one contiguous run of 32 * dim * k floats.  It reads the run with
+// whole float4 loads into shared memory (plus the 32 new observations and, if asked, the 32 terminal
+// observations), and writes the updated run back with whole float4 stores: every global access is a
+// full 128-byte line.  The previous version walked one private 96-byte row per thread (24 scalar
+// loads and stores at a 96-byte lane stride).  In place is safe: a warp reads its whole run before it
+// writes any of it, and runs of different warps are disjoint.
+__global__ void __launch_bounds__(256) k_frame_stack_warp(float* __restrict__ stacked, const float* __restrict__ obs,
+                                                          int64_t es, int64_t cs, const uint8_t* __restrict__ done,
+                                                          const float* __restrict__ term_in, int64_t tes, int64_t tcs,
+                                                          float* __restrict__ term_out, int64_t n, int dim, int k) {
+  extern __shared__ __align__(16) float sm_fs[];   // per warp: [32 * rowlen] old rows | [32 * dim] obs | [32 * dim] term
+  const unsigned lane = threadIdx.x & 31u;
+  const int rowlen = dim * k, keep = rowlen - dim;
+  const int per_warp = 32 * rowlen + 64 * dim;
+  float* sm_old = sm_fs + (threadIdx.x >> 5) * per_warp;
+  float* sm_obs = sm_old + 32 * rowlen;
+  float* sm_term = sm_obs + 32 * dim;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (row0 >= n) return;
+  const int rows = (int)(n - row0 >= 32 ? 32 : n - row0);
+  const int nflt = rows * rowlen;
+  float* run = stacked + row0 * rowlen;
+  const bool vec = (((uintptr_t)run) & 15) == 0;
+  if (vec) {
+    for (int q = (int)lane * 4; q + 3 < nflt; q += 128)
+      *reinterpret_cast<float4*>(sm_old + q) = *reinterpret_cast<const float4*>(run + q);
+    for (int q = (nflt & ~3) + (int)lane; q < nflt; q += 32) sm_old[q] = run[q];
+  } else {
+    for (int q = (int)lane; q < nflt; q += 32) sm_old[q] = run[q];
+  }
+  const bool mine = (int)lane < rows;
+  const bool d = mine && done != nullptr && done[row0 + lane] != 0;
+  const unsigned any_done = __ballot_sync(0xffffffffu, d);
+  if (mine) {
+    for (int c = 0; c < dim; ++c) sm_obs[lane * dim + c] = obs[(row0 + lane) * es + c * cs];
+    if (term_out != nullptr && any_done)
+      for (int c = 0; c < dim; ++c) sm_term[lane * dim + c] = term_in[(row0 + lane) * tes + c * tcs];
+  }
+  __syncwarp();
+  const unsigned done_mask = any_done;
+  auto new_val = [&](int q) -> float {
+    const int r = q / rowlen, j = q - r * rowlen;
+    if (j >= keep) return sm_obs[r * dim + (j - keep)];
+    return ((done_mask >> r) & 1u) ? 0.0f : sm_old[q + dim];
+  };
+  if (vec) {
+    for (int q = (int)lane * 4; q + 3 < nflt; q += 128) {
+      float4 v;
+      v.x = new_val(q); v.y = new_val(q + 1); v.z = new_val(q + 2); v.w = new_val(q + 3);
+      *reinterpret_cast<float4*>(run + q) = v;
+    }
+    for (int q = (nflt & ~3) + (int)lane; q < nflt; q += 32) run[q] = new_val(q);
+  } else {
+    for (int q = (int)lane; q < nflt; q += 32) run[q] = new_val(q);
+  }
+  if (term_out != nullptr && any_done) {
+    // rows of envs that did not finish are not meaningful and never read (same convention as term_obs)
+    float* trun = term_out + row0 * rowlen;
+    for (int q = (int)lane; q < nflt; q += 32) {
+      const int r = q / rowlen, j = q - r * rowlen;
+      trun[q] = j >= keep ? sm_term[r * dim + (j - keep)] : sm_old[q + dim];
+    }
+  }
+}
+
+// fallback for very long rows (shared memory): one thread per row
 __global__ void __launch_bounds__(256) k_frame_stack(float* __restrict__ stacked, const float* __restrict__ obs,
                                                      int64_t es, int64_t cs, const uint8_t* __restrict__ done,
-                                                     int64_t n, int dim, int k) {
+                                                     const float* __restrict__ term_in, int64_t tes, int64_t tcs,
+                                                     float* __restrict__ term_out, int64_t n, int dim, int k) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float* row = stacked + i * (int64_t)(dim * k);
   const bool d = done != nullptr && done[i] != 0;
+  if (d && term_out != nullptr) {
+    float* trow = term_out + i * (int64_t)(dim * k);
+    for (int j = 0; j < dim * (k - 1); ++j) trow[j] = row[j + dim];
+    for (int c = 0; c < dim; ++c) trow[dim * (k - 1) + c] = term_in[i * tes + c * tcs];
+  }
   for (int j = 0; j < dim * (k - 1); ++j) row[j] = d ? 0.0f : row[j + dim];
   for (int c = 0; c < dim; ++c) row[dim * (k - 1) + c] = obs[i * es + c * cs];
 }
@@ -171,8 +265,23 @@ extern "C" int cl_obs_moments(void* stream, const float* obs, int64_t es, int64_
   const int block = 256;
   int64_t blocks = (n + block - 1) / block;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (dim <= 8) k_moments<8><<<(unsigned)blocks, block, 0, st>>>(obs, es, cs, n, dim, shift, out2d);
-  else k_moments<32><<<(unsigned)blocks, block, 0, st>>>(obs, es, cs, n, dim, shift, out2d);
+  if (dim <= 8) k_moments<8, float><<<(unsigned)blocks, block, 0, st>>>(obs, es, cs, n, dim, shift, out2d);
+  else k_moments<32, float><<<(unsigned)blocks, block, 0, st>>>(obs, es, cs, n, dim, shift, out2d);
+  return fail_if(cudaGetLastError());
+}
+
+// float64 input (SB3 feeds VecNormalize's float64 discounted returns to ret_rms.update)
+extern "C" int cl_moments_f64(void* stream, const double* x, int64_t es, int64_t cs, int64_t n, int32_t dim,
+                              const double* shift, double* out2d) {
+  if (!x || !shift || !out2d || dim < 1 || dim > 32 || n < 1) return CL_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(out2d, 0, sizeof(double) * 2 * (size_t)dim, st);
+  if (e != cudaSuccess) return CL_ECUDA;
+  const int block = 256;
+  int64_t blocks = (n + block - 1) / block;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dim <= 8) k_moments<8, double><<<(unsigned)blocks, block, 0, st>>>(x, es, cs, n, dim, shift, out2d);
+  else k_moments<32, double><<<(unsigned)blocks, block, 0, st>>>(x, es, cs, n, dim, shift, out2d);
   return fail_if(cudaGetLastError());
 }
 
@@ -211,18 +320,45 @@ extern "C" int cl_obs_normalize(void* stream, const float* in, int64_t ies, int6
                                 double epsilon, double clip) {
   if (!in || !out || !mean || !var || dim < 1 || n < 1) return CL_EINVAL;
   const int block = 256;
-  k_normalize<<<(unsigned)((n + block - 1) / block), block, 0, (cudaStream_t)stream>>>(in, ies, ics, out, oes, ocs,
-                                                                                         n, dim, mean, var, epsilon, clip);
+  const unsigned grid = (unsigned)((n + block - 1) / block);
+  const bool rows = oes == dim && ocs == 1 && (((uintptr_t)out) & 15) == 0 && dim <= 48;
+  if (rows)
+    k_normalize<true><<<grid, block, (size_t)(block / 32) * 32 * dim * sizeof(float), (cudaStream_t)stream>>>(
+        in, ies, ics, out, oes, ocs, n, dim, mean, var, epsilon, clip);
+  else
+    k_normalize<false><<<grid, block, 0, (cudaStream_t)stream>>>(in, ies, ics, out, oes, ocs, n, dim, mean, var,
+                                                                  epsilon, clip);
+  return fail_if(cudaGetLastError());
+}
+
+static int frame_stack_launch(cudaStream_t st, float* stacked, const float* obs, int64_t es, int64_t cs,
+                              const uint8_t* done, const float* term_in, int64_t tes, int64_t tcs, float* term_out,
+                              int64_t n, int32_t dim, int32_t n_stack) {
+  const int block = 256, wpb = block / 32;
+  const size_t smem = (size_t)wpb * (32 * (size_t)dim * n_stack + 64 * (size_t)dim) * sizeof(float);
+  if (smem <= 48 * 1024) {
+    const int64_t warps = (n + 31) / 32;
+    k_frame_stack_warp<<<(unsigned)((warps + wpb - 1) / wpb), block, smem, st>>>(stacked, obs, es, cs, done, term_in, tes,
+                                                                                 tcs, term_out, n, dim, n_stack);
+  } else {
+    k_frame_stack<<<(unsigned)((n + block - 1) / block), block, 0, st>>>(stacked, obs, es, cs, done, term_in, tes, tcs,
+                                                                          term_out, n, dim, n_stack);
+  }
   return fail_if(cudaGetLastError());
 }
 
 extern "C" int cl_frame_stack(void* stream, float* stacked, const float* obs, int64_t es, int64_t cs,
                               const uint8_t* done, int64_t n, int32_t dim, int32_t n_stack) {
   if (!stacked || !obs || dim < 1 || n_stack < 1 || n < 1) return CL_EINVAL;
-  const int block = 256;
-  k_frame_stack<<<(unsigned)((n + block - 1) / block), block, 0, (cudaStream_t)stream>>>(stacked, obs, es, cs, done, n,
-                                                                                           dim, n_stack);
-  return fail_if(cudaGetLastError());
+  return frame_stack_launch((cudaStream_t)stream, stacked, obs, es, cs, done, nullptr, 0, 0, nullptr, n, dim, n_stack);
+}
+
+extern "C" int cl_frame_stack_term(void* stream, float* stacked, const float* obs, int64_t es, int64_t cs,
+                                   const uint8_t* done, const float* term_obs, int64_t tes, int64_t tcs,
+                                   float* term_stacked, int64_t n, int32_t dim, int32_t n_stack) {
+  if (!stacked || !obs || !done || !term_obs || !term_stacked || dim < 1 || n_stack < 1 || n < 1) return CL_EINVAL;
+  return frame_stack_launch((cudaStream_t)stream, stacked, obs, es, cs, done, term_obs, tes, tcs, term_stacked, n, dim,
+                            n_stack);
 }
 
 extern "C" int cl_eval_metrics(void* stream, const double* err, const double* ctrl, int32_t T, int32_t n_err,

@@ -60,6 +60,16 @@ def eval_metrics(err: torch.Tensor, ctrl: torch.Tensor, dt: float, error_band: f
     return {"mae": out[:, 0], "rmse": out[:, 1], "settling_time": out[:, 2], "energy": out[:, 3]}
 
 
+def base_batch(env):
+    """The ChaosBatch under any stack of device wrappers (walks `.venv` until `.batch` is found)."""
+    e = env
+    while not hasattr(e, "batch"):
+        if not hasattr(e, "venv"):
+            raise AttributeError(f"{type(env).__name__} wraps no BatchedChaosVecEnv")
+        e = e.venv
+    return e.batch
+
+
 class RunningMeanStd:
     """SB3 RunningMeanStd (float64 mean/var/count, Chan et al. parallel update).  Batch moments and
     the merge both run on the device and update `mean` / `var` / `count_t` in place: no host
@@ -81,14 +91,17 @@ class RunningMeanStd:
         self.count_t.fill_(float(v))
 
     def update(self, x: torch.Tensor) -> None:
-        """x: f32 [N, dim] (any strides)."""
+        """x: f32 or f64 [N, dim] (any strides)."""
         lib = L.load()
         n, dim = x.shape
         dev = x.device
+        if x.dtype not in (torch.float32, torch.float64):
+            raise ValueError("RunningMeanStd.update expects float32 or float64")
         with torch.cuda.device(dev):
             st = _stream(dev)
-            L.check(lib.cl_obs_moments(st, _p(x), x.stride(0), x.stride(1), n, dim, _p(self.mean),
-                                       _p(self._acc)), None, "cl_obs_moments")
+            fn, name = (lib.cl_obs_moments, "cl_obs_moments") if x.dtype == torch.float32 else \
+                (lib.cl_moments_f64, "cl_moments_f64")
+            L.check(fn(st, _p(x), x.stride(0), x.stride(1), n, dim, _p(self.mean), _p(self._acc)), None, name)
             L.check(lib.cl_rms_update(st, _p(self._acc), n, dim, _p(self.mean), _p(self.var), _p(self.count_t)),
                     None, "cl_rms_update")
 
@@ -104,7 +117,7 @@ class DeviceVecNormalize:
         self.norm_obs, self.norm_reward = norm_obs, norm_reward
         self.clip_obs, self.clip_reward, self.gamma, self.epsilon = clip_obs, clip_reward, gamma, epsilon
         self.num_envs = venv.num_envs
-        b = venv.batch
+        b = base_batch(venv)
         self.device = b.device
         self.obs_rms = RunningMeanStd((b.obs_dim,), self.device)
         self.ret_rms = RunningMeanStd((1,), self.device)
@@ -147,15 +160,17 @@ class DeviceVecNormalize:
         if self.training and self.norm_obs:
             self.obs_rms.update(obs)
         nobs = self.normalize_obs(obs, self._out)
-        if self.training and self.norm_reward:
+        if self.training:
+            # SB3 VecNormalize.step_wait -> _update_reward: whenever `training`, float64 returns
             self.returns.mul_(self.gamma).add_(rew)      # in place: replayable as a captured graph
-            self.ret_rms.update(self.returns.float().view(-1, 1))
+            self.ret_rms.update(self.returns.view(-1, 1))
         nrew = self.normalize_reward(rew)
         self.returns.masked_fill_(done != 0, 0.0)
         return nobs, nrew, done
 
     def terminal_obs(self) -> torch.Tensor:
-        return self.normalize_obs(self.venv.batch.terminal_obs(), self._term)
+        inner = self.venv.terminal_obs() if hasattr(self.venv, "terminal_obs") else base_batch(self.venv).terminal_obs()
+        return self.normalize_obs(inner, self._term)
 
     def get_original_obs(self) -> torch.Tensor:
         return self.old_obs
@@ -171,21 +186,32 @@ class DeviceVecNormalize:
 
 
 class DeviceVecFrameStack:
-    """VecFrameStack(n_stack) for 1-D observations, stacked along the last axis, on device."""
+    """VecFrameStack(n_stack) for 1-D observations, stacked along the last axis, on device.
+    Wraps a BatchedChaosVecEnv or a DeviceVecNormalize (code/lorenz_filter/train.py:109-115)."""
 
     def __init__(self, venv, n_stack: int):
         self.venv, self.n_stack = venv, int(n_stack)
         self.num_envs = venv.num_envs
-        src = venv.venv.batch if hasattr(venv, "venv") else venv.batch
+        src = base_batch(venv)
         self.dim = src.obs_dim
         self.device = src.device
         self.stacked = torch.zeros((self.num_envs, self.dim * self.n_stack), dtype=torch.float32, device=self.device)
+        self._term = torch.zeros_like(self.stacked)
 
-    def _push(self, obs: torch.Tensor, done: Optional[torch.Tensor]) -> torch.Tensor:
+    def _inner_terminal_obs(self) -> torch.Tensor:
+        return self.venv.terminal_obs() if hasattr(self.venv, "terminal_obs") else base_batch(self.venv).terminal_obs()
+
+    def _push(self, obs: torch.Tensor, done: Optional[torch.Tensor], term: Optional[torch.Tensor] = None) -> torch.Tensor:
         lib = L.load()
         with torch.cuda.device(self.device):
-            L.check(lib.cl_frame_stack(_stream(self.device), _p(self.stacked), _p(obs), obs.stride(0), obs.stride(1),
-                                       _p(done), self.num_envs, self.dim, self.n_stack), None, "cl_frame_stack")
+            if term is None or done is None:
+                L.check(lib.cl_frame_stack(_stream(self.device), _p(self.stacked), _p(obs), obs.stride(0), obs.stride(1),
+                                           _p(done), self.num_envs, self.dim, self.n_stack), None, "cl_frame_stack")
+            else:
+                L.check(lib.cl_frame_stack_term(_stream(self.device), _p(self.stacked), _p(obs), obs.stride(0),
+                                                obs.stride(1), _p(done), _p(term), term.stride(0), term.stride(1),
+                                                _p(self._term), self.num_envs, self.dim, self.n_stack), None,
+                        "cl_frame_stack_term")
         return self.stacked
 
     def reset_tensor(self) -> torch.Tensor:
@@ -195,7 +221,13 @@ class DeviceVecFrameStack:
 
     def step_tensor(self, actions: torch.Tensor):
         obs, rew, done = self.venv.step_tensor(actions)
-        return self._push(obs, done), rew, done
+        return self._push(obs, done, self._inner_terminal_obs()), rew, done
+
+    def terminal_obs(self) -> torch.Tensor:
+        """[N, dim * n_stack]: for envs that finished an episode in the last step, the stacked terminal
+        observation of SB3's StackedObservations.update (previous stack rolled by one frame + the inner
+        env's -- normalised, if wrapped -- terminal observation).  Other rows are undefined."""
+        return self._term
 
 
 class DeviceRolloutCollector:
@@ -217,7 +249,7 @@ class DeviceRolloutCollector:
                  use_cuda_graph: bool = False):
         self.env, self.policy, self.n_steps = env, policy, int(n_steps)
         self.gamma, self.gae_lambda = gamma, gae_lambda
-        b = env.venv.batch if hasattr(env, "venv") else env.batch
+        b = base_batch(env)
         self.batch, dev, N, T = b, b.device, b.num_envs, self.n_steps
         self.obs_dim = env.stacked.shape[1] if hasattr(env, "stacked") else b.obs_dim
         self.buf = {

@@ -299,6 +299,10 @@ int cl_obs_moments(void* stream, const float* obs, int64_t es, int64_t cs, int64
  * acc2d[2][dim] for a batch of n rows into mean[dim], var[dim] and the device scalar *count. */
 int cl_rms_update(void* stream, const double* acc2d, int64_t n, int32_t dim, double* mean, double* var,
                   double* count);
+/* cl_obs_moments for float64 input: VecNormalize feeds its float64 discounted returns to
+ * ret_rms.update (SB3 2.7.1 common/vec_env/vec_normalize.py::VecNormalize._update_reward). */
+int cl_moments_f64(void* stream, const double* x, int64_t es, int64_t cs, int64_t n, int32_t dim,
+                   const double* shift, double* out2d);
 int cl_obs_normalize(void* stream, const float* in, int64_t ies, int64_t ics, float* out, int64_t oes,
                      int64_t ocs, int64_t n, int32_t dim, const double* mean, const double* var,
                      double epsilon, double clip);
@@ -308,6 +312,13 @@ int cl_obs_normalize(void* stream, const float* in, int64_t ies, int64_t ics, fl
  * observation is written into the last frame. */
 int cl_frame_stack(void* stream, float* stacked, const float* obs, int64_t es, int64_t cs,
                    const uint8_t* done, int64_t n, int32_t dim, int32_t n_stack);
+/* The same update that also produces, for envs with done[i] != 0, the stacked terminal observation
+ * SB3 puts into infos[i]["terminal_observation"] (StackedObservations.update: the previous stack
+ * rolled by one frame with the env's terminal observation as its last frame): term_obs f32 addressed
+ * t[i*tes + c*tcs], term_stacked f32 [n][dim*n_stack] row-major (rows of unfinished envs: undefined). */
+int cl_frame_stack_term(void* stream, float* stacked, const float* obs, int64_t es, int64_t cs,
+                        const uint8_t* done, const float* term_obs, int64_t tes, int64_t tcs,
+                        float* term_stacked, int64_t n, int32_t dim, int32_t n_stack);
 
 /* Evaluation metrics of code/lorenz_pmsm/test_evaluate.py:25-59,239-250 for n trajectories at once:
  * err f64 [T][n_err][stride], ctrl f64 [T][n_ctrl][stride] -> out4 f64 [n][4] =

@@ -154,3 +154,62 @@ def memristive4_pair():
 def pmsm_free():
     """lorenz_singlecontrol.py::lorenzEnv_transient (uncontrolled noisy PMSM; step() has no action)."""
     return load("lorenz_singlecontrol.py").lorenzEnv_transient()
+
+
+# ---- the reference's evaluation metrics (code/lorenz_pmsm/test_evaluate.py) -------------------
+
+EVAL_SCRIPT = os.path.join(REF_ROOT, "code", "lorenz_pmsm", "test_evaluate.py")
+
+
+def load_eval_script() -> types.ModuleType:
+    """Execute code/lorenz_pmsm/test_evaluate.py unmodified (module level only: imports, rcParams,
+    function definitions; its __main__ block does not run).  Needs stubs for the SB3 / matplotlib /
+    env_utils / gym_lorenz imports at its top; pandas is real."""
+    key = "lorenz_pmsm/test_evaluate.py"
+    if key in _CACHE:
+        return _CACHE[key]
+    if not os.path.exists(EVAL_SCRIPT):
+        raise FileNotFoundError(EVAL_SCRIPT)
+    _install_stubs()
+    sys.modules["matplotlib.pyplot"].rcParams = {}
+    sb3 = sys.modules["stable_baselines3"]
+    sb3.A2C = object
+    for name, attrs in (("stable_baselines3.common", {}),
+                        ("stable_baselines3.common.vec_env", {"DummyVecEnv": object, "VecNormalize": object}),
+                        ("stable_baselines3.common.monitor", {"Monitor": object})):
+        sys.modules.setdefault(name, _module(name, **attrs))
+    sys.modules.setdefault("env_utils", _module("env_utils", make_env=None))
+    sys.modules.setdefault("gym_lorenz", _module("gym_lorenz"))
+    path_before = list(sys.path)
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_lorenz_pmsm_test_evaluate", EVAL_SCRIPT)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path[:] = path_before        # the script appends its gym-lorenz directory
+    _CACHE[key] = mod
+    return mod
+
+
+def eval_steady_block():
+    """The steady-state MAE / RMSE / settling-time block of test_evaluate.py (:239-250 -- inline code
+    of the evaluation loop, not a function) compiled from the reference file's own lines.  Returns
+    f(arr_e1, arr_e2, arr_e3, arr_u1, arr_u2, dt) -> (mae, rmse, max_ts, energy)."""
+    import textwrap
+    mod = load_eval_script()
+    lines = open(EVAL_SCRIPT, encoding="utf-8").read().splitlines()
+    first = next(k for k, ln in enumerate(lines) if "actual_steady_start = min(1000" in ln)
+    last = next(k for k, ln in enumerate(lines) if "max_ts = np.nanmax([ts1, ts2, ts3])" in ln)
+    assert 0 < last - first < 20
+    code = compile(textwrap.dedent("\n".join(lines[first:last + 1])), EVAL_SCRIPT + f":{first + 1}-{last + 1}", "exec")
+
+    def run(arr_e1, arr_e2, arr_e3, arr_u1, arr_u2, dt):
+        ns = {"np": np, "calculate_advanced_metrics": mod.calculate_advanced_metrics, "arr_e1": arr_e1,
+              "arr_e2": arr_e2, "arr_e3": arr_e3, "arr_u1": arr_u1, "arr_u2": arr_u2, "dt": dt}
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")          # np.nanmax of all-NaN settling times warns
+            exec(code, ns)
+        return ns["mae"], ns["rmse"], ns["max_ts"], ns["energy"]
+
+    return run

@@ -170,9 +170,81 @@ def gen_xlsx_kat(outdir):
     np.savez_compressed(os.path.join(outdir, "pmsm_xlsx_kat.npz"), **out)
 
 
+def eval_inputs(rng, T, K):
+    """Synthetic sync-error / control trajectories shaped like the evaluation script's (decaying
+    oscillation + noise), with the three special cases of the settling-time logic."""
+    t = np.arange(T)[:, None, None]
+    tau = rng.uniform(20, 400, size=(1, 3, K))
+    e = rng.uniform(0.5, 30, size=(1, 3, K)) * np.exp(-t / tau) * np.cos(t / 7.0) + 0.01 * rng.normal(size=(T, 3, K))
+    e[-1, 0, 0] = 1.0          # trajectory 0: component 0 never settles
+    e[-1, :, 1] = 1.0          # trajectory 1: nothing settles -> NaN
+    e[:, :, 2] = 0.001         # trajectory 2: never leaves the band -> 0
+    u = rng.normal(size=(T, 2, K)) * 50
+    return e.astype(np.float32).astype(np.float64), u.astype(np.float32).astype(np.float64)   # compact fixture
+
+
+def gen_eval_metrics(outdir):
+    """calculate_advanced_metrics + the steady-state block of code/lorenz_pmsm/test_evaluate.py
+    (:25-59, :239-250), executed from the reference file itself (oracle/ref_loader.py)."""
+    block = R.eval_steady_block()
+    rng = np.random.default_rng(77)
+    out = {}
+    for tag, T, K, dt in (("long", 2200, 10, 0.001), ("short", 1200, 10, 0.01)):
+        e, u = eval_inputs(rng, T, K)
+        res = np.array([block(e[:, 0, k], e[:, 1, k], e[:, 2, k], u[:, 0, k], u[:, 1, k], dt) for k in range(K)])
+        out.update({f"{tag}_err": e.astype(np.float32), f"{tag}_ctrl": u.astype(np.float32), f"{tag}_dt": np.float64(dt),
+                    f"{tag}_metrics": res})          # columns: mae, rmse, max settling time, energy
+    np.savez_compressed(os.path.join(outdir, "eval_metrics.npz"), **out)
+    print("wrote eval_metrics:", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})
+
+
+DERIV_KINDS = [("lorenz3", 3, (-30, 30)), ("lorenz3_pair", 3, (-20, 20)), ("lorenz4_pair", 4, (0, 5)),
+               ("pmsm_classic", 3, (-10, 10)), ("pmsm_single", 3, (-20, 20))]
+
+
+def gen_derivatives(outdir):
+    """Right-hand sides as the reference evaluates them.  Classic envs: after step(), env.state0 =
+    [state1_new, f(state1_new)] (e.g. dynamic.py:77-80, lorenz_env_transient.py:332-339,
+    lorenz_env_transient_pmsm.py:107-112) -- pairs (state, derivative) harvested from stepping the
+    unmodified env.  HR: the module-level hr_derivatives (lorenz_env_try.py:7-12) called directly with
+    the env's constants and controls (a1, a2) = clip(a)*100 as step() forms them (:92-93)."""
+    rng = np.random.default_rng(4242)
+    out = {}
+    for kind, dim, (lo, hi) in DERIV_KINDS:
+        S, D = [], []
+        ns = {"lorenz3": 4, "lorenz3_pair": 10, "lorenz4_pair": 9, "pmsm_classic": 7, "pmsm_single": 4}[kind]
+        for k in range(48):
+            env = RC.make_reference(kind)
+            st = make_ic(rng, kind, ns, lo, hi, {})
+            RC.inject(kind, env, st)
+            na = 2 if kind.startswith("pmsm") else 3
+            for t in range(6):
+                with np.errstate(all="ignore"):
+                    env.step(rng.uniform(-0.05, 0.05, na).astype(np.float32))
+                s0 = np.asarray(env.state0, np.float64)
+                S.append(s0[:dim]); D.append(s0[dim:2 * dim])
+        out[f"{kind}_state"], out[f"{kind}_deriv"] = np.array(S), np.array(D)
+    mod = R.load("lorenz_env_try.py")
+    env = R.hr_sync()
+    x = rng.uniform(-3, 3, (256, 3))
+    act = rng.uniform(-1.3, 1.3, (256, 2)).astype(np.float32)
+    a12 = np.clip(act, -1.0, 1.0) * 100.0                 # float32, as lorenz_env_try.py:92-93
+    assert a12.dtype == np.float32
+    d = np.array([mod.hr_derivatives(x[k], a12[k, 0], a12[k, 1], env.a, env.b, env.c, env.d, env.r, env.s,
+                                     env.I_bias, env.x_rest) for k in range(256)], np.float64)
+    d0 = np.array([mod.hr_derivatives(x[k], 0, 0, env.a, env.b, env.c, env.d, env.r, env.s, env.I_bias, env.x_rest)
+                   for k in range(256)], np.float64)
+    out.update({"hr_sync_state": x, "hr_sync_action": act, "hr_sync_control": a12.astype(np.float32),
+                "hr_sync_deriv": d, "hr_sync_deriv_free": d0})
+    np.savez_compressed(os.path.join(outdir, "derivatives.npz"), **out)
+    print("wrote derivatives:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if not R.available():
         sys.exit("reference tree not found; golden vectors can only be regenerated where it exists")
     gen_cfg1(HERE)
     gen_parity(HERE)
     gen_xlsx_kat(HERE)
+    gen_eval_metrics(HERE)
+    gen_derivatives(HERE)

@@ -108,7 +108,9 @@ def test_lorenz_rk4_f32_vs_oracle(oracle_api):
     a = np.random.default_rng(0).uniform(-1, 1, (n, 3)).astype(np.float32)
     b.step(torch.as_tensor(a, device=b.device))
     o.step(np.ascontiguousarray(a.T))
-    H.assert_close(b.state.cpu().numpy()[:3], o.state[:3], 2e-5, "f32 rk4 state", atol=1e-5)
+    # float32 round-off only (the oracle integrates the same scheme in float32, in the textbook form; the
+    # kernel on the shifted coordinate z - rho): a few ulp(32) = 3.8e-6 per substep on states of scale 30
+    H.assert_close(b.state.cpu().numpy()[:3], o.state[:3], 2e-5, "f32 rk4 state", atol=4e-5)
     b.close()
 
 
