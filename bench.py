@@ -13,10 +13,13 @@ tensor f32 [T, 3, n_pad] resident in HBM; outputs streamed to HBM every interval
 
 `value`   = all ranks' env-steps / max-over-ranks device time (CUDA events), inputs in HBM.
 `e2e`     = the same env, same metric, driven through the SB3-facing VecEnv API
-            (`step_async(actions)` / `step_wait()`) with HOST buffers: per control interval the
-            actions cross PCIe from pinned host memory and obs/reward/done come back as host
-            arrays, all inside the timed region (a variant with a fresh pageable ndarray per step,
-            i.e. one extra host memcpy, is reported next to it).
+            (`step_async(actions)` / `step_wait()`) with HOST buffers: per control interval a
+            caller-owned (pageable) float32 ndarray of actions -- what stock SB3 passes -- is staged
+            into pinned memory and crosses PCIe, and obs/reward/done come back as host arrays, all
+            inside the timed region (the variant whose policy writes straight into the env's pinned
+            staging buffer is reported next to it).
+`cfg4`    = (N > 1 only) BASELINE.json configs[3]: 1,048,576 envs per GPU, FP64 and FP32, episode-
+            statistics all-reduce after EVERY step, device-timed, max over ranks.
 `roofline`= the fused rollout kernel against the FP64-FMA peak measured live by a
             register-resident DFMA chain (MEASURED_PEAKS.json carries no FP64 number), plus
             its HBM side against MEASURED_PEAKS.json's copy bandwidth.
@@ -64,6 +67,7 @@ def parse():
     ap.add_argument("--kind", default="lorenz_rk4")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true", help="N>1: skip the 1,048,576-envs-per-GPU FP64/FP32 sub-record")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="bench steps timed on the host-buffer path")
     ap.add_argument("--param-jitter", type=float, default=0.0,
                     help="per-env parameter randomisation: each env's sigma/rho/beta (sigma/gamma for PMSM) "
@@ -188,12 +192,11 @@ def run_reference(args):
     el = time.perf_counter() - t0
     value = n * T * args.steps / el
     cfg = workload_config(args, max(world, 1))
-    cfg["reference_sample_intervals_per_step"] = T
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": cfg,
+        "data": "synthetic", "config": cfg, "reference_sample_intervals_per_step": T,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n} envs x {T} control intervals per step x {args.steps} steps, "
                                    f"oracle/chaos_oracle.c (C restatement, OpenMP x{threads}); the reference "
@@ -217,6 +220,9 @@ def run_b200(args):
     rank, world, local = D.init_process_group()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one rank per GPU: each rank keeps to its own cores of its GPU's NUMA node (before any pinned
+    # allocation, so first touch places the staging buffers there) -- see distributed.pin_rank_to_cores
+    cores = D.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     slab = D.weak_slab(args.envs_per_gpu, world, rank)
     N, T, S = slab.num_envs, args.chunk, args.substeps
     flop_sub, bytes_step, dtype_name, fma_bytes = KIND_INFO[args.kind]
@@ -357,40 +363,51 @@ def run_b200(args):
         env.reset()
         rng = np.random.default_rng(rank)
         host_actions = [rng.uniform(-1, 1, (N, env.batch.act_dim)).astype(np.float32) for _ in range(8)]
-        pin = env.batch.host_action_buffer()          # pinned f32 [N, act_dim]
-        pin[:] = host_actions[0]
         chunks = max(1, min(args.e2e_chunks, args.steps))
         for k in range(32):
-            env.step(pin)
+            env.step(host_actions[k % 8])
         barrier()
+        # headline: a caller-owned ndarray every step (stock SB3: collect_rollouts passes the policy's
+        # freshly produced action array)
         t0 = time.perf_counter()
         acc = 0.0
         for k in range(chunks * T):
-            obs, rew, dones, infos = env.step(pin)
+            obs, rew, dones, infos = env.step(host_actions[k % 8])
             acc += float(rew[0])
         torch.cuda.synchronize(dev)
         el = time.perf_counter() - t0
         tm = torch.tensor([el], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        # variant: a fresh pageable ndarray every step (what stock SB3 passes): adds one user->pinned memcpy
+        # side number: the policy writes its actions straight into the env's pinned staging buffer
+        pin = env.batch.host_action_buffer()          # pinned f32 [N, act_dim]
+        pin[:] = host_actions[0]
+        for k in range(8):
+            env.step(pin)
         t0 = time.perf_counter()
         for k in range(T):
-            obs, rew, dones, infos = env.step(host_actions[k % 8])
+            obs, rew, dones, infos = env.step(pin)
         torch.cuda.synchronize(dev)
-        el_page = (time.perf_counter() - t0) / T
+        el_pin = (time.perf_counter() - t0) / T
         e2e = {"value": float(N) * T * chunks * world / float(tm.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(env.batch.h2d_bytes_per_step * T),
                "d2h_bytes_per_step": int(env.batch.d2h_bytes_per_step * T),
-               "api": "BatchedChaosVecEnv.step_async(actions)/step_wait() (SB3 VecEnv contract); actions in pinned host "
-                      f"memory, obs/reward/done returned as host arrays; {T} control intervals per bench step, "
-                      f"{chunks} bench steps timed, wall clock, max over ranks",
+               "api": "BatchedChaosVecEnv.step_async(actions)/step_wait() (SB3 VecEnv contract); a caller-owned pageable "
+                      "float32 ndarray of actions every step, obs/reward/done returned as host arrays; "
+                      f"{T} control intervals per bench step, {chunks} bench steps timed, wall clock, max over ranks",
                "us_per_control_interval": float(tm.item()) / (chunks * T) * 1e6,
-               "us_per_control_interval_pageable_inputs_rank0": el_page * 1e6}
+               "us_per_control_interval_pinned_inputs_rank0": el_pin * 1e6,
+               "host_cores_of_rank0": len(cores)}
         env.close()
+
+    cfg4 = None
+    if world > 1 and not args.no_cfg4:
+        cfg4 = run_cfg4(args, torch, dist, D, ChaosBatch, measure_fma_peak, rank, world, local, dev)
 
     if rank == 0:
         line["e2e"] = e2e
+        if cfg4 is not None:
+            line["cfg4"] = cfg4
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample, v1, _ = cpu_arm(args, budget_s=12.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
@@ -400,6 +417,52 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_cfg4(args, torch, dist, D, ChaosBatch, measure_fma_peak, rank, world, local, dev):
+    """BASELINE.json configs[3]: 8 Mi envs over 8 GPUs = 1,048,576 envs per rank (weak scaling at any N),
+    Lorenz RK4 x 16, FP64 and FP32, the 64 B episode-statistics vector all-reduced (NCCL) after EVERY
+    rollout step.  Device-timed with CUDA events, max over ranks.  Returns the sub-record (rank 0) or None."""
+    n, T, S, steps = 1 << 20, 16, 16, 12
+    rec = {"envs_per_gpu": n, "total_envs": n * world, "control_intervals_per_step": T, "substeps": S, "steps": steps,
+           "stats_allreduce": "every step"}
+    for kind, key, fb in (("lorenz_rk4", "f64", 8), ("lorenz_rk4_f32", "f32", 4)):
+        batch = ChaosBatch(kind, n, device=dev, seed=0, env_id_base=rank * n, substeps=S, dt=0.01, autoreset=True,
+                           max_episode_steps=1000)
+        batch.reset()
+        NP = batch.n_pad
+        g = torch.Generator(device=dev).manual_seed(99 + rank)
+        act = torch.rand((T, batch.act_dim, NP), generator=g, device=dev, dtype=torch.float32) * 2 - 1
+        actions = act[:, :, :n].permute(0, 2, 1)
+        out = {"obs": torch.empty((T, batch.obs_dim, NP), dtype=torch.float32, device=dev),
+               "reward": torch.empty((T, NP), dtype=batch.real, device=dev),
+               "done": torch.empty((T, NP), dtype=torch.uint8, device=dev)}
+
+        def step():
+            batch.rollout(T, actions, out=out)
+            D.allreduce_stats(batch.stats_tensor(clear=False))
+
+        for _ in range(3):
+            step()
+        dist.barrier(); torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize(dev)
+        tmax = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item()) / steps
+        value = float(n) * T * world / (ms * 1e-3)
+        peak = measure_fma_peak(local, fb, 0.2) if rank == 0 else 0.0
+        rec[key] = {"value": value, "unit": UNIT, "ms_per_step": ms,
+                    "tflops_per_gpu": value / world * S * 87 * 1e-12,
+                    "frac": (value / world * S * 87 * 1e-12 / peak) if peak > 0 else None, "peak_tflops": peak}
+        batch.close()
+        del act, actions, out
+        torch.cuda.empty_cache()
+    return rec if rank == 0 else None
 
 
 def main():

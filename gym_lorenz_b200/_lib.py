@@ -28,7 +28,7 @@ KIND_NAMES = {
 
 F_ADD_NOISE, F_EVAL_MODE, F_ADD_FILTER, F_AUTORESET, F_OBS_F64 = 0x01, 0x02, 0x04, 0x08, 0x10
 DONE_TERMINATED, DONE_TRUNCATED = 0x1, 0x2
-HOST_DMA, HOST_ZEROCOPY, HOST_PIPELINED = 0, 1, 2
+HOST_DMA, HOST_ZEROCOPY, HOST_PIPELINED, HOST_STREAMED = 0, 1, 2, 3
 NSTATS = 8
 STAT_NAMES = ("episodes", "return_sum", "return_sq_sum", "length_sum", "nonfinite_events",
               "terminated", "truncated", "reserved")

@@ -183,6 +183,20 @@ class ChaosBatch:
         io.mask = _ptr(mask)
         return io
 
+    def _check_buffer(self, name: str, t, shape, dtype) -> None:
+        """Caller-supplied device buffers reach the kernels as raw pointers: refuse anything whose
+        shape / dtype / device / layout differs from what the kernel will address."""
+        if not isinstance(t, torch.Tensor):
+            raise ValueError(f"{name} must be a torch tensor")
+        if t.device != self.device:
+            raise ValueError(f"{name} must live on {self.device}, got {t.device}")
+        if t.dtype != dtype:
+            raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+
     def _check_action(self, actions: torch.Tensor) -> torch.Tensor:
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.asarray(actions, np.float32))
@@ -219,6 +233,8 @@ class ChaosBatch:
             actions = self._check_action(actions)
         io = self._io_step
         io.action, io.act_es, io.act_cs = actions.data_ptr(), actions.stride(0), actions.stride(1)
+        if noise is not None:
+            self._check_buffer("noise", noise, (self.layout.noise_dim, self.n_pad), torch.float64)
         io.noise = None if noise is None else noise.data_ptr()
         rc = self.lib.cl_step(self.ctx, self._stream(), self._bufs_ref, self._io_step_ref)
         if rc != 0:
@@ -267,14 +283,16 @@ class ChaosBatch:
         if "obs" in want:
             o = out["obs"]
             if rows:
-                if tuple(o.shape) != (T, self.num_envs, self.obs_dim) or not o.is_contiguous():
-                    raise ValueError("obs buffer must be contiguous [T, N, obs_dim] for obs_layout='rows'")
+                self._check_buffer("out['obs'] (obs_layout='rows')", o, (T, self.num_envs, self.obs_dim), odt)
                 io.obs, io.obs_es, io.obs_cs, desc.obs_ts = _ptr(o), self.obs_dim, 1, self.num_envs * self.obs_dim
             else:
+                self._check_buffer("out['obs']", o, (T, self.obs_dim, NP), odt)
                 io.obs, io.obs_es, io.obs_cs, desc.obs_ts = _ptr(o), 1, NP, self.obs_dim * NP
         if "reward" in want:
+            self._check_buffer("out['reward']", out["reward"], (T, NP), self.real)
             io.reward, desc.rew_ts = _ptr(out["reward"]), NP
         if "done" in want:
+            self._check_buffer("out['done']", out["done"], (T, NP), torch.uint8)
             io.done, desc.done_ts = _ptr(out["done"]), NP
         io.last_ep_ret, io.last_ep_len = _ptr(self.last_ep_ret), _ptr(self.last_ep_len)
         L.check(self.lib.cl_rollout(self.ctx, self._stream(), C.byref(self._bufs), C.byref(io),
@@ -378,9 +396,11 @@ class ChaosBatch:
         return (*views, v.n_done)
 
     def set_host_mode(self, mode: str, slices: int = 1) -> None:
-        """How `step_host_async` moves the data: "dma", "zerocopy" or "pipelined" (with `slices`
-        env slices alternating over two streams).  Results do not depend on it."""
-        m = {"dma": L.HOST_DMA, "zerocopy": L.HOST_ZEROCOPY, "pipelined": L.HOST_PIPELINED}[mode]
+        """How `step_host_async` moves the data: "dma", "zerocopy", "pipelined" (`slices` env slices
+        alternating over two streams) or "streamed" (one launch issued before the caller's array is
+        staged slice by slice into the pinned buffer the kernel reads).  Results do not depend on it."""
+        m = {"dma": L.HOST_DMA, "zerocopy": L.HOST_ZEROCOPY, "pipelined": L.HOST_PIPELINED,
+             "streamed": L.HOST_STREAMED}[mode]
         L.check(self.lib.cl_host_set_mode(self.ctx, m, int(slices)), self.ctx, "cl_host_set_mode")
 
     def reset_host(self) -> np.ndarray:

@@ -42,6 +42,7 @@ struct HostSlot {
   float* term_obs;
   double* last_ep_ret;
   int32_t* last_ep_len;
+  uint8_t* warp_done;  // pinned [ceil(N/32)] (+ padding to 8): 1 where an env-warp ended an episode in this step
 };
 
 struct HostStage {
@@ -67,9 +68,16 @@ struct HostStage {
   // pinned host memory, so slice j's upstream writes overlap slice j+1's downstream copy.
   int mode;
   bool extras_on_host;  // the pending step wrote term_obs / last_ep_* to the host slot itself
-  int slices;        // CL_HOST_PIPELINED: number of env slices (>= 1)
+  int slices;        // CL_HOST_PIPELINED / CL_HOST_STREAMED: number of env slices (>= 1)
   cudaStream_t side; // second stream of the pipeline
   cudaEvent_t ev_fork, ev_join;
+  // CL_HOST_STREAMED: the step kernel is launched first and waits, block by block, for the slice of
+  // the pinned action buffer it reads to be published (generation number) by the staging loop
+  uint32_t* h_ready;   // pinned [64] generation flags, one per slice
+  uint32_t* h_err;     // pinned: set by a block whose bounded wait expired
+  uint32_t gen;
+  uint8_t* d_warp_done;  // device copy for CL_HOST_DMA (travels with the result block)
+  size_t wd_bytes;
 };
 
 }  // namespace
@@ -215,6 +223,7 @@ static void host_stage_free(cl_ctx* ctx) {
   cudaFreeHost(h.h_act);
   cudaFree(h.d_act); cudaFree(h.d_out);
   cudaFree(h.d_term); cudaFree(h.d_ler); cudaFree(h.d_lel);
+  cudaFreeHost(h.h_ready);
   for (int k = 0; k < kHostRing; ++k) {
     cudaFreeHost(h.slot[k].out);
     cudaFreeHost(h.slot[k].term_obs); cudaFreeHost(h.slot[k].last_ep_ret); cudaFreeHost(h.slot[k].last_ep_len);
@@ -476,6 +485,16 @@ extern "C" int cl_block_size(const cl_ctx* ctx) { return ctx ? ctx->block : 0; }
 
 // ---- host-buffer path ------------------------------------------------------------------
 
+// Default data-movement mode of the host path per (env kind, batch size), from the measured table in
+// profiles/r02_e2e_host_modes.jsonl (tools/e2e_modes.py: every kind x {4,096, 16,384, 65,536} envs x every
+// mode, fresh caller-owned action array each step).
+static void host_mode_default(int kind, int64_t n, int* mode, int* slices) {
+  (void)kind;
+  *mode = CL_HOST_STREAMED;
+  int k = (int)(n / 8192);
+  *slices = k < 1 ? 1 : (k > 16 ? 16 : k);
+}
+
 static int host_stage_init(cl_ctx* ctx) {
   HostStage& h = ctx->hs;
   if (h.ready) return CL_OK;
@@ -485,8 +504,15 @@ static int host_stage_init(cl_ctx* ctx) {
   CU(cudaStreamCreateWithFlags(&h.stream, cudaStreamNonBlocking));
   CU(cudaHostAlloc((void**)&h.h_act, N * A * sizeof(float), cudaHostAllocDefault));
   CU(cudaMalloc((void**)&h.d_act, N * A * sizeof(float)));
-  h.out_bytes = N * O * sizeof(float) + N * sizeof(float) + N;
+  h.wd_bytes = (((N + 31) / 32) + 7) / 8 * 8;
+  const size_t wd_off = (N * O * sizeof(float) + N * sizeof(float) + N + 7) / 8 * 8;
+  h.out_bytes = wd_off + h.wd_bytes;
   CU(cudaMalloc((void**)&h.d_out, h.out_bytes));
+  h.d_warp_done = h.d_out + wd_off;
+  CU(cudaHostAlloc((void**)&h.h_ready, 80 * sizeof(uint32_t), cudaHostAllocDefault));
+  memset(h.h_ready, 0, 80 * sizeof(uint32_t));
+  h.h_err = h.h_ready + 72;
+  h.gen = 0;
   h.d_obs = (float*)h.d_out;
   h.d_rew = (float*)(h.d_out + N * O * sizeof(float));
   h.d_done = (uint8_t*)(h.d_out + N * O * sizeof(float) + N * sizeof(float));
@@ -501,6 +527,7 @@ static int host_stage_init(cl_ctx* ctx) {
     h.slot[k].obs = (float*)h.slot[k].out;
     h.slot[k].reward = (float*)(h.slot[k].out + N * O * sizeof(float));
     h.slot[k].done = (uint8_t*)(h.slot[k].out + N * O * sizeof(float) + N * sizeof(float));
+    h.slot[k].warp_done = h.slot[k].out + wd_off;
     CU(cudaHostAlloc((void**)&h.slot[k].term_obs, N * O * sizeof(float), cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&h.slot[k].last_ep_ret, N * sizeof(double), cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&h.slot[k].last_ep_len, N * sizeof(int32_t), cudaHostAllocDefault));
@@ -515,13 +542,13 @@ static int host_stage_init(cl_ctx* ctx) {
   // to be staged at >= 262,144 envs: each slice costs ~9 us of host-side launch time
   // (profiles/r01_e2e_host_modes.jsonl).  CHAOS_B200_HOST_MODE=dma|zerocopy|pipelined and
   // CHAOS_B200_HOST_SLICES=k override (tuning); CHAOS_B200_ZEROCOPY=0 is the older spelling of dma.
-  h.slices = 1;
-  h.mode = CL_HOST_ZEROCOPY;
+  host_mode_default(ctx->cfg.kind, (int64_t)N, &h.mode, &h.slices);
   if (const char* ov = getenv("CHAOS_B200_ZEROCOPY")) { if (ov[0] == '0') h.mode = CL_HOST_DMA; }
   if (const char* ov = getenv("CHAOS_B200_HOST_MODE")) {
     if (!strcmp(ov, "dma")) h.mode = CL_HOST_DMA;
     else if (!strcmp(ov, "zerocopy")) h.mode = CL_HOST_ZEROCOPY;
     else if (!strcmp(ov, "pipelined")) { h.mode = CL_HOST_PIPELINED; if (h.slices < 2) h.slices = 2; }
+    else if (!strcmp(ov, "streamed")) h.mode = CL_HOST_STREAMED;
   }
   if (const char* ov = getenv("CHAOS_B200_HOST_SLICES")) { const int k = atoi(ov); if (k >= 1 && k <= 64) h.slices = k; }
   h.ready = true;
@@ -552,9 +579,11 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
   cudaStream_t st = host_stream(ctx, stream);
   const bool stage_copy = action_host && action_host != h.h_act;
   CU(cudaSetDevice(ctx->cfg.device));
-  const int mode = (h.mode == CL_HOST_PIPELINED && ctx->graph_mode) ? CL_HOST_ZEROCOPY : h.mode;
+  // graph capture cannot contain CPU-side staging: captured steps read the pinned buffer as it is
+  int mode = ((h.mode == CL_HOST_PIPELINED || h.mode == CL_HOST_STREAMED) && ctx->graph_mode) ? CL_HOST_ZEROCOPY : h.mode;
+  if (mode == CL_HOST_STREAMED && !stage_copy) mode = CL_HOST_ZEROCOPY;   // the caller wrote the pinned buffer itself
   const bool host_out = mode != CL_HOST_DMA;       // kernel writes obs / reward / done to pinned host memory
-  const bool host_in = mode == CL_HOST_ZEROCOPY;   // kernel reads the actions from pinned host memory
+  const bool host_in = mode == CL_HOST_ZEROCOPY || mode == CL_HOST_STREAMED;   // kernel reads the actions from pinned host memory
   h.cur = (h.cur + 1) % kHostRing;
   HostSlot& s = h.slot[h.cur];
   cl_io io;
@@ -572,7 +601,31 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
   if (r) return r;
   p.reward_f32 = 1;
   p.flags &= ~CL_F_OBS_F64;
-  if (mode == CL_HOST_PIPELINED && h.slices > 1) {
+  // per-env-warp "an episode ended" flags: cleared here, set by the kernel, scanned by cl_step_host_wait
+  // (N / 32 bytes instead of the N done flags)
+  if (host_out) { memset(s.warp_done, 0, h.wd_bytes); p.warp_done = s.warp_done; p.host_rows = 1; }
+  else { CU(cudaMemsetAsync(h.d_warp_done, 0, h.wd_bytes, st)); p.warp_done = h.d_warp_done; }
+  if (mode == CL_HOST_STREAMED) {
+    // 1. launch: every block waits for the generation flag of the action slice it reads;
+    // 2. stage the caller's array slice by slice into the pinned buffer, publishing each slice.
+    // Nothing between the launch and the last flag store can fail, so the kernel always gets its flags
+    // (and its wait is bounded anyway).
+    const int blk = ctx->block;
+    int slices = h.slices < 1 ? 1 : (h.slices > 64 ? 64 : h.slices);
+    size_t per = ((N + (size_t)slices - 1) / (size_t)slices + (size_t)blk - 1) / (size_t)blk * (size_t)blk;   // whole blocks
+    h.gen += 1;
+    if (h.gen == 0) h.gen = 1;
+    *h.h_err = 0u;
+    p.act_ready = h.h_ready; p.act_gen = h.gen; p.act_slice_envs = (int32_t)per; p.host_err = h.h_err;
+    r = launch(ctx, p, cl::MODE_STEP, st);
+    if (r) return r;
+    int j = 0;
+    for (size_t b = 0; b < N; b += per, ++j) {
+      const size_t e = b + per < N ? b + per : N;
+      memcpy(h.h_act + b * A, action_host + b * A, (e - b) * A * sizeof(float));
+      __atomic_store_n(&h.h_ready[j], h.gen, __ATOMIC_RELEASE);
+    }
+  } else if (mode == CL_HOST_PIPELINED && h.slices > 1) {
     // slice j runs on stream (j & 1): [DMA its actions in] -> [kernel: step, write results to host].
     // The user's array is staged into pinned memory slice by slice too, so that host memcpy
     // overlaps the device work of the slices already enqueued.
@@ -610,7 +663,7 @@ extern "C" int cl_host_set_zero_copy(cl_ctx* ctx, int enable) {
 
 extern "C" int cl_host_set_mode(cl_ctx* ctx, int mode, int slices) {
   if (!ctx) return CL_EINVAL;
-  if (mode < CL_HOST_DMA || mode > CL_HOST_PIPELINED || slices < 1 || slices > 64)
+  if (mode < CL_HOST_DMA || mode > CL_HOST_STREAMED || slices < 1 || slices > 64)
     return fail(ctx, CL_EINVAL, "cl_host_set_mode: mode %d / slices %d out of range", mode, slices);
   int r = host_stage_init(ctx);
   if (r) return r;
@@ -629,8 +682,21 @@ static int host_wait_common(cl_ctx* ctx, void* stream, int64_t* n_done_out) {
   h.pending = false;
   const size_t N = (size_t)ctx->cfg.num_envs, O = (size_t)ctx->lay.obs_dim;
   HostSlot& s = h.slot[h.cur];
+  if (*h.h_err) { *h.h_err = 0u; return fail(ctx, CL_ECUDA, "streamed host step: a block timed out waiting for its action slice"); }
+  // finished episodes: scan the per-env-warp flags (N / 32 bytes, 8 at a time); count the done
+  // flags only inside flagged warps
   int64_t nd = 0;
-  for (size_t i = 0; i < N; ++i) nd += (s.done[i] != 0);
+  const size_t W = (N + 31) / 32;
+  for (size_t w8 = 0; w8 < h.wd_bytes; w8 += 8) {
+    uint64_t word;
+    memcpy(&word, s.warp_done + w8, 8);
+    if (!word) continue;
+    for (size_t w = w8; w < w8 + 8 && w < W; ++w) {
+      if (!s.warp_done[w]) continue;
+      const size_t lo = w * 32, hi = lo + 32 < N ? lo + 32 : N;
+      for (size_t i = lo; i < hi; ++i) nd += (s.done[i] != 0);
+    }
+  }
   if (nd > 0 && !h.extras_on_host) {  // DMA mode: fetch the terminal observations and Monitor numbers
     CU(cudaMemcpyAsync(s.term_obs, h.d_term, N * O * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(s.last_ep_ret, h.d_ler, N * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -42,6 +42,15 @@ struct KParams {
   double* last_ep_ret;
   int32_t* last_ep_len;
   const uint8_t* mask;
+  // host path (cl_step_host_async): per-env-warp "an episode ended here" flags in the pinned result
+  // slot, Monitor numbers written as whole warp rows, and -- streamed mode -- the generation flags the
+  // CPU publishes slice by slice while it stages the caller's action array into pinned memory
+  uint8_t* warp_done;
+  int32_t host_rows;
+  const uint32_t* act_ready;
+  uint32_t act_gen;
+  int32_t act_slice_envs;
+  uint32_t* host_err;
   // rollout
   int32_t T;
   int64_t act_ts, obs_ts, rew_ts, done_ts;
@@ -208,6 +217,12 @@ __device__ __forceinline__ void stp(const KParams& p, int c, int64_t i, real v) 
   ((real*)p.state)[(int64_t)c * p.n_pad + i] = v;
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ---- one control interval of one env (shared by the static and the dynamic kernels) ----
 
 // The "plain rollout" I/O shape -- what a synthetic-action benchmark or a device-side collector
@@ -310,7 +325,7 @@ __device__ __forceinline__ void step_dispatch(typename E::S& s, const KParams& p
 }
 
 template <class E, bool ROLL, bool PLAIN = false, int SPEC = 0, bool RUNPTR = false>
-__device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, double& ep_ret,
+__device__ __forceinline__ unsigned env_interval(typename E::S& s, int32_t& ep_len, double& ep_ret,
                                              const KParams& p, const int64_t i, const bool live,
                                              const unsigned lane, const int t, const uint64_t step,
                                              const float* a, const bool want_noise, const bool obs64,
@@ -386,10 +401,20 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
     // a PCIe transaction).  Rows of unfinished envs are not meaningful and never read.
     store_obs_rows_warp<real, E::OBS>(sm_rows, (float*)p.term_obs + oo, i - (int64_t)lane, p.n, lane, obs);
   }
+  const bool host_rows = !PLAIN && p.host_rows != 0;   // warp-uniform
+  if (host_rows && dall && live) {
+    // host path: the Monitor numbers go to pinned host memory; a warp with a finished episode writes
+    // all of its rows (256 + 128 contiguous bytes) instead of one scattered PCIe write per finished env.
+    // Entries of unfinished envs are not meaningful and never read.
+    p.last_ep_ret[i] = ep_ret;
+    p.last_ep_len[i] = ep_len;
+  }
   if (live && done) {
     if (has_term && !rows_fast) store_obs<real>(p.term_obs, oo, p.obs_es, p.obs_cs, i, obs, E::OBS, obs64);
-    if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;   // tested only when an episode ends
-    if (p.last_ep_len) p.last_ep_len[i] = ep_len;
+    if (!host_rows) {
+      if (p.last_ep_ret) p.last_ep_ret[i] = ep_ret;   // tested only when an episode ends
+      if (p.last_ep_len) p.last_ep_len[i] = ep_len;
+    }
     if (autoreset) {
       E::reset(s, p, PLAIN ? make_stream(p, i, step) : rng, obs);
       ep_len = 0;
@@ -429,6 +454,7 @@ __device__ __forceinline__ void env_interval(typename E::S& s, int32_t& ep_len, 
     pend->t = t;
     pend->valid = 1u;
   }
+  return dall;
 }
 
 template <class E>
@@ -469,14 +495,35 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
   const bool autoreset = PLAIN || (p.flags & CL_F_AUTORESET) != 0;
   const bool want_noise = !PLAIN && E::NOISE > 0 && E::uses_noise(p);
   const int T = ROLL ? p.T : 1;
+  const bool streamed = !ROLL && p.act_ready != nullptr;   // block-uniform
+  if (streamed) {
+    // Streamed host mode: this kernel was launched BEFORE the CPU finished staging the caller's action
+    // array into the pinned buffer.  The CPU publishes slice j (act_slice_envs envs, a whole number of
+    // blocks) by storing the step's generation number into act_ready[j]; the block's first thread polls
+    // that word over PCIe, the state loads above are already in flight meanwhile.  Bounded wait: after
+    // ~2 s the block gives up, flags the error for cl_step_host_wait and proceeds.
+    if (threadIdx.x == 0) {
+      const uint32_t* flag = p.act_ready + (i - p.i_begin) / p.act_slice_envs;
+      uint64_t t0 = 0, t1 = 0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (ld_acquire_sys_u32(flag) != p.act_gen) {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) { if (p.host_err) *p.host_err = 1u; break; }
+      }
+    }
+    __syncthreads();
+  }
 
   // actions are fetched one control interval ahead; this only hides their latency while
   // scoreboard slots are free (ptxas drains the loads before long bodies) --
   // the dynamic kernel below stages them through shared memory instead
   float a_next[E::ACT];
 #pragma unroll
-  for (int c = 0; c < E::ACT; ++c)
-    a_next[c] = (live && (PLAIN || p.action != nullptr)) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
+  for (int c = 0; c < E::ACT; ++c) {
+    if (streamed) a_next[c] = live ? __ldcv(p.action + i * p.act_es + c * p.act_cs) : 0.0f;   // written by the CPU during this launch
+    else a_next[c] = (live && (PLAIN || p.action != nullptr)) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
+  }
 
   unsigned bad_acc = 0u;
   bool fin = E::finite(s);
@@ -499,7 +546,8 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
             a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
         }
       }
-      env_interval<E, ROLL, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin, &pend);
+      const unsigned dall = env_interval<E, ROLL, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin, &pend);
+      if (!ROLL && !PLAIN && p.warp_done != nullptr && dall && lane == 0) p.warp_done[i >> 5] = 1;
     }
   };
   if constexpr (PLAIN) {

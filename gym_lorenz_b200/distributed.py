@@ -12,7 +12,7 @@ from __future__ import annotations
 import math
 import os
 from dataclasses import dataclass
-from typing import Dict, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -62,6 +62,90 @@ def init_process_group(backend: Optional[str] = None) -> Tuple[int, int, int]:
             kw["device_id"] = torch.device("cuda", local)
         dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
     return rank, world, local
+
+
+# ---- CPU placement of the ranks --------------------------------------------------------------
+# The SB3-facing host path (step_async / step_wait with host buffers) is driven by one Python thread
+# per rank and moves ~2.7 MB per step through pinned host memory.  With 8 ranks on one box and no
+# placement, the ranks' threads migrate over all cores of both sockets and their pinned buffers end up
+# on whichever NUMA node first touched them: measured e2e scaling efficiency 0.53 at 8 GPUs (round 1).
+# Each rank therefore pins itself to its own share of the cores of the NUMA node its GPU hangs off,
+# BEFORE it allocates pinned memory (first touch then places the buffers on that node).
+
+def _parse_cpulist(text: str) -> List[int]:
+    out: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            lo, hi = part.split("-")
+            out.extend(range(int(lo), int(hi) + 1))
+        else:
+            out.append(int(part))
+    return out
+
+
+def plan_affinity(allowed: Sequence[int], gpu_nodes: Sequence[int], node_cpus: Dict[int, Sequence[int]],
+                  local_rank: int) -> List[int]:
+    """Cores for `local_rank` (one rank per GPU, rank r drives GPU r).  `gpu_nodes[r]` is the NUMA node of
+    GPU r (-1 = unknown), `node_cpus[n]` the logical CPUs of node n, `allowed` this process's current
+    affinity mask.  Ranks whose GPUs share a node split that node's allowed cores contiguously and
+    evenly; unknown topology falls back to an even split of `allowed` over all ranks.  Never returns
+    an empty set."""
+    allowed = sorted(set(int(c) for c in allowed))
+    world = len(gpu_nodes)
+    if world <= 1 or not allowed:
+        return allowed
+    node = gpu_nodes[local_rank]
+    local = sorted(set(node_cpus.get(node, ())) & set(allowed)) if node >= 0 else []
+    peers = [r for r in range(world) if gpu_nodes[r] == node]
+    if not local or len(local) < len(peers):
+        local, peers = allowed, list(range(world))      # no usable topology: share everything evenly
+    k = peers.index(local_rank)
+    q, rem = divmod(len(local), len(peers))
+    lo = k * q + min(k, rem)
+    hi = lo + q + (1 if k < rem else 0)
+    return local[lo:hi] if hi > lo else [local[k % len(local)]]
+
+
+def gpu_numa_topology(world: int) -> Tuple[List[int], Dict[int, List[int]]]:
+    """(NUMA node of each of the first `world` GPUs, cpu list per node) from sysfs; -1 / {} where unknown."""
+    nodes: List[int] = []
+    cpus: Dict[int, List[int]] = {}
+    for r in range(world):
+        node = -1
+        try:
+            pr = torch.cuda.get_device_properties(r)
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+                node = int(f.read().strip())
+        except Exception:  # noqa: BLE001
+            node = -1
+        nodes.append(node)
+        if node >= 0 and node not in cpus:
+            try:
+                with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                    cpus[node] = _parse_cpulist(f.read())
+            except Exception:  # noqa: BLE001
+                pass
+    return nodes, cpus
+
+
+def pin_rank_to_cores(local_rank: int, local_world: int) -> List[int]:
+    """Pin the calling process (all its current threads inherit on creation) to this rank's cores.
+    Call it before the first pinned allocation.  Returns the cores chosen (the old mask if world is 1)."""
+    allowed = sorted(os.sched_getaffinity(0))
+    if local_world <= 1:
+        return allowed
+    nodes, cpus = gpu_numa_topology(local_world)
+    mine = plan_affinity(allowed, nodes, cpus, local_rank)
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return allowed
+    # intra-op thread pools sized for the whole box would oversubscribe the rank's share
+    torch.set_num_threads(max(1, min(torch.get_num_threads(), len(mine))))
+    return mine
 
 
 def allreduce_stats(stats: torch.Tensor, async_op: bool = False):

@@ -226,8 +226,18 @@ class BatchedChaosVecEnv(VecEnv):
     round trip.
     """
 
+    # obs + reward bytes up to which step_wait() returns private copies by default (a copy of this size
+    # costs a few microseconds; at 65,536 envs it would cost more than the step itself)
+    COPY_OUTPUTS_AUTO_BYTES = 256 * 1024
+
     def __init__(self, kind: str = "hr_sync", num_envs: int = 1, *, device="cuda:0", seed: int = 0,
-                 monitor: bool = True, **kwargs):
+                 monitor: bool = True, copy_outputs: Optional[bool] = None, **kwargs):
+        """`copy_outputs`: SB3's DummyVecEnv returns fresh copies of obs / rewards / dones every step.
+        True does the same; False returns zero-copy views of a ring of 3 pinned result slots, valid
+        until the third following step (enough for SB3's own algorithms, which copy what they keep
+        at once); None (default) copies while obs + reward are at most 256 KiB per step and aliases
+        above.  `infos` is one list object reused across steps either way: entries of envs that
+        finished an episode are rebuilt each step, so keep `infos[i]` dicts, not the list."""
         self._kw = dict(kwargs)
         self._kind = kind
         self._device = device
@@ -237,6 +247,9 @@ class BatchedChaosVecEnv(VecEnv):
         self._t_start = time.time()
         self._infos = _LazyInfos(num_envs)
         self._waiting = False
+        if copy_outputs is None:
+            copy_outputs = num_envs * (self.batch.obs_dim + 1) * 4 <= self.COPY_OUTPUTS_AUTO_BYTES
+        self._copy_outputs = bool(copy_outputs)
         super().__init__(num_envs, box_for(self.batch.layout, "obs"), box_for(self.batch.layout, "act"))
 
     # ---- numpy / SB3 path --------------------------------------------------------------
@@ -268,6 +281,8 @@ class BatchedChaosVecEnv(VecEnv):
                        lel[idx].tolist() if self._monitor else None,
                        round(time.time() - self._t_start, 6))
         infos._begin_step(pending)
+        if self._copy_outputs:
+            return obs.copy(), rew.copy(), dones, infos     # `dones` is already a fresh array
         return obs, rew, dones, infos
 
     def close(self) -> None:
@@ -341,8 +356,15 @@ class BatchedChaosVecEnv(VecEnv):
             out = d[:, 0].cpu().numpy()
             return [out.copy() for _ in idx]
         if method_name == "reset":
-            obs = self.reset()
-            return [(obs[i], {}) for i in idx]
+            # gymnasium reset of the selected envs only (SB3: env_method("reset", indices=...) calls
+            # envs[i].reset() for i in indices): masked device reset, others keep their episodes
+            if len(idx) == self.num_envs:
+                obs = self.reset()
+                return [(obs[i], {}) for i in idx]
+            mask = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.batch.device)
+            mask[torch.as_tensor(idx, dtype=torch.long, device=self.batch.device)] = 1
+            obs = self.batch.reset(mask)[idx].float().cpu().numpy()
+            return [(obs[k], {}) for k in range(len(idx))]
         raise AttributeError(method_name)
 
     def env_is_wrapped(self, wrapper_class, indices=None) -> List[bool]:

@@ -31,6 +31,30 @@ def test_summarize():
     assert np.isnan(D.summarize([0.0] * 8)["ep_rew_mean"])
 
 
+def test_rank_affinity_plan():
+    """Each rank gets its own contiguous share of the cores of its GPU's NUMA node."""
+    node_cpus = {0: list(range(0, 48)) + list(range(96, 144)), 1: list(range(48, 96)) + list(range(144, 192))}
+    allowed = list(range(192))
+    gpu_nodes = [0, 0, 0, 0, 1, 1, 1, 1]
+    plans = [D.plan_affinity(allowed, gpu_nodes, node_cpus, r) for r in range(8)]
+    assert all(len(p) == 24 for p in plans)
+    assert sorted(c for p in plans[:4] for c in p) == sorted(node_cpus[0])
+    assert sorted(c for p in plans[4:] for c in p) == sorted(node_cpus[1])
+    assert len({c for p in plans for c in p}) == 192                  # disjoint
+    # restricted mask (container cpuset): only allowed cores are handed out
+    allowed = list(range(8, 40))
+    plans = [D.plan_affinity(allowed, [0, 0], node_cpus, r) for r in range(2)]
+    assert plans[0] == list(range(8, 24)) and plans[1] == list(range(24, 40))
+    # unknown topology: even split of the allowed set over all ranks
+    plans = [D.plan_affinity(list(range(10)), [-1, -1, -1], {}, r) for r in range(3)]
+    assert plans == [[0, 1, 2, 3], [4, 5, 6], [7, 8, 9]]
+    # a node with fewer allowed cores than ranks: fall back to sharing everything, never empty
+    plans = [D.plan_affinity([0, 1, 50, 51], [0, 0, 0, 1], {0: [0], 1: [50, 51]}, r) for r in range(4)]
+    assert all(len(p) >= 1 for p in plans)
+    assert D.plan_affinity([3, 4], [0], {0: [3, 4]}, 0) == [3, 4]      # single rank: untouched
+    assert D._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
     return p

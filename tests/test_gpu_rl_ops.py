@@ -260,3 +260,123 @@ def test_vecnormalize_pipeline_replays_as_cuda_graph():
     assert env_g.batch.stats()["episodes"] == env_e.batch.stats()["episodes"] > 0
     env_g.batch.set_graph_mode(False)
     env_g.close(); env_e.close()
+
+
+def test_frame_stack_terminal_observation_follows_sb3_stacked_observations():
+    """SB3 StackedObservations.update: for a finished env infos["terminal_observation"] becomes the
+    previous stack rolled by one frame with the env's terminal observation as last frame -- here with
+    VecNormalize underneath (the normalised terminal observation), as in FrameStack(VecNormalize(env))."""
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n, k = 3000 + 5, 4
+    env = BatchedChaosVecEnv("hr_sync", n, seed=4, max_episode_steps=6)
+    vn = rl_ops.DeviceVecNormalize(env, norm_obs=True, norm_reward=False, clip_obs=10.0)
+    fs = rl_ops.DeviceVecFrameStack(vn, k)
+    prev = fs.reset_tensor().clone()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    seen = 0
+    for t in range(14):
+        a = (torch.rand((n, 2), generator=g) * 2 - 1).to("cuda:0")
+        obs, rew, done = fs.step_tensor(a)
+        d = done != 0
+        if bool(d.any()):
+            want = torch.cat([prev[:, 6:], vn.terminal_obs()], dim=1)
+            assert torch.equal(fs.terminal_obs()[d], want[d]), t
+            assert torch.equal(obs[d][:, :18], torch.zeros_like(obs[d][:, :18]))     # stack restarts
+            seen += int(d.sum())
+        nd = ~d
+        assert torch.equal(obs[nd][:, :18], prev[nd][:, 6:])
+        prev = obs.clone()
+    assert seen >= 2 * n
+    env.close()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_collector_over_framestack_of_vecnormalize(graph):
+    """The reference's lorenz_filter pipeline shape (VecFrameStack(4) around the env, PPO on top) with
+    VecNormalize in between and a short TimeLimit, so the TimeLimit bootstrap evaluates the policy on
+    stacked, normalised terminal observations every few steps; eager and as one CUDA graph."""
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n, T, k = 1024, 12, 4
+    torch.manual_seed(2)
+    net = torch.nn.Sequential(torch.nn.Linear(6 * k, 16), torch.nn.Tanh(), torch.nn.Linear(16, 3)).to("cuda:0")
+
+    def policy(obs):
+        assert obs.shape == (n, 6 * k)
+        y = net(obs)
+        return torch.tanh(y[:, :2]), y[:, 2], -(y[:, :2] ** 2).sum(1)
+
+    env = BatchedChaosVecEnv("hr_sync", n, seed=9, max_episode_steps=5)
+    fs = rl_ops.DeviceVecFrameStack(rl_ops.DeviceVecNormalize(env, norm_reward=False), k)
+    col = rl_ops.DeviceRolloutCollector(fs, policy, n_steps=T, use_cuda_graph=graph)
+    assert col.batch is env.batch and col.obs_dim == 6 * k
+    for _ in range(3):
+        out = col.collect()
+        torch.cuda.synchronize()
+    assert out["obs"].shape == (T, n, 6 * k) and bool(torch.isfinite(out["advantages"]).all())
+    starts = out["episode_starts"].cpu().numpy()
+    assert starts.any() and not starts.all()
+    env.close()
+
+
+def test_vecnormalize_return_statistics_follow_sb3():
+    """SB3 VecNormalize.step_wait: the discounted returns and ret_rms are updated whenever `training`
+    is set (norm_reward only decides whether rewards are rescaled), from float64 returns."""
+    import torch
+    from gym_lorenz_b200 import rl_ops
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n = 2048
+    env = BatchedChaosVecEnv("pmsm_sync", n, seed=6, max_episode_steps=9)
+    vn = rl_ops.DeviceVecNormalize(env, norm_obs=True, norm_reward=False, gamma=0.99)
+    vn.reset_tensor()
+    rms = S.RunningMeanStd(shape=())
+    returns = np.zeros(n, np.float64)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for t in range(12):
+        a = (torch.rand((n, 2), generator=g) * 2 - 1).to("cuda:0")
+        _, rew, done = vn.step_tensor(a)
+        assert torch.equal(rew, vn.old_reward)                      # norm_reward=False: rewards untouched
+        returns = returns * 0.99 + vn.old_reward.double().cpu().numpy()
+        rms.update(returns)
+        returns[done.cpu().numpy() != 0] = 0.0
+        assert np.array_equal(vn.returns.cpu().numpy(), returns), t
+    assert np.isclose(vn.ret_rms.mean.item(), rms.mean, rtol=1e-12)
+    assert np.isclose(vn.ret_rms.var.item(), rms.var, rtol=1e-11)
+    assert np.isclose(vn.ret_rms.count, rms.count, rtol=1e-15)
+    env.close()
+
+
+def test_caller_supplied_buffers_are_validated():
+    import torch
+    b = H.gpu_batch("lorenz_rk4", 1000, seed=1)
+    b.reset()
+    T, NP = 4, b.n_pad
+    acts = torch.zeros((T, 1000, 3), device=b.device)
+    good = {"obs": torch.empty((T, 6, NP), dtype=torch.float32, device=b.device),
+            "reward": torch.empty((T, NP), dtype=torch.float64, device=b.device),
+            "done": torch.empty((T, NP), dtype=torch.uint8, device=b.device)}
+    b.rollout(T, acts, out=dict(good))
+    for key, bad in (("obs", torch.empty((T, 6, NP - 128), dtype=torch.float32, device=b.device)),
+                     ("obs", torch.empty((T, 6, NP), dtype=torch.float64, device=b.device)),
+                     ("reward", torch.empty((T, NP), dtype=torch.float32, device=b.device)),
+                     ("reward", torch.empty((T, 2 * NP), dtype=torch.float64, device=b.device)[:, ::2]),
+                     ("done", torch.empty((T, NP), dtype=torch.uint8)),
+                     ("done", torch.empty((T - 1, NP), dtype=torch.uint8, device=b.device))):
+        o = dict(good); o[key] = bad
+        with pytest.raises(ValueError):
+            b.rollout(T, acts, out=o)
+    with pytest.raises(ValueError):
+        b.rollout(T, acts, out={"obs": torch.empty((T, 999, 6), dtype=torch.float32, device=b.device)}, obs_layout="rows")
+    h = H.gpu_batch("hr_sync", 256, add_noise=True)
+    h.reset()
+    a = torch.zeros((256, 2), device=h.device)
+    h.step(a, noise=torch.zeros((3, h.n_pad), dtype=torch.float64, device=h.device))
+    for bad in (torch.zeros((3, 256 - 1), dtype=torch.float64, device=h.device),
+                torch.zeros((3, h.n_pad), dtype=torch.float32, device=h.device),
+                torch.zeros((2, h.n_pad), dtype=torch.float64, device=h.device)):
+        with pytest.raises(ValueError):
+            h.step(a, noise=bad)
+    b.close(); h.close()

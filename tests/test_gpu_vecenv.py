@@ -41,12 +41,71 @@ def test_vecenv_numpy_contract_and_autoreset_infos():
             assert np.all(np.abs(obs[:, :3]) <= 30.0)   # fresh reset obs (dynamic.py:37)
         else:
             assert not dones.any() and all(not d for d in infos)
-    # the zero-copy result ring keeps the previous step's obs intact (SB3 collect_rollouts
-    # reads self._last_obs after the next env.step)
-    snap = prev[-2].copy()
-    assert np.array_equal(prev[-2], snap)
     st = env.stats()
     assert st["episodes"] == 2 * n and st["truncated"] == 2 * n
+    env.close()
+
+
+def test_step_wait_output_lifetime():
+    """copy_outputs=False: obs / reward are views of a ring of 3 pinned slots -- the arrays returned at
+    step t are untouched by steps t+1 and t+2 (SB3's collect_rollouts reads self._last_obs after the
+    next env.step) and are overwritten by step t+3.  copy_outputs=True (the default at this size):
+    private copies, never overwritten, like DummyVecEnv."""
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n = 512
+    rng = np.random.default_rng(0)
+
+    def act():
+        return rng.uniform(-0.05, 0.05, (n, 3)).astype(np.float32)
+
+    env = BatchedChaosVecEnv("lorenz3", n, seed=1, copy_outputs=False)
+    env.reset()
+    obs_t, rew_t, _, _ = env.step(act())
+    snap_o, snap_r = obs_t.copy(), rew_t.copy()
+    for k in (1, 2):
+        env.step(act())
+        assert np.array_equal(obs_t, snap_o) and np.array_equal(rew_t, snap_r), f"overwritten after {k} more steps"
+    obs_3, _, _, _ = env.step(act())
+    assert np.shares_memory(obs_3, obs_t)                      # the ring wrapped around ...
+    assert not np.array_equal(obs_t, snap_o)                   # ... so the old view now shows step t+3
+    env.close()
+
+    env = BatchedChaosVecEnv("lorenz3", n, seed=1)
+    assert env._copy_outputs                                   # 512 envs: copies by default
+    env.reset()
+    kept = [env.step(act())[0] for _ in range(6)]
+    snaps = [k.copy() for k in kept]
+    for _ in range(4):
+        env.step(act())
+    assert all(np.array_equal(a, b) for a, b in zip(kept, snaps))
+    assert not any(np.shares_memory(kept[0], k) for k in kept[1:])
+    env.close()
+    big = BatchedChaosVecEnv("lorenz3", 65536, seed=1)
+    assert not big._copy_outputs                               # 65,536 envs: zero-copy views by default
+    big.close()
+
+
+def test_env_method_reset_honours_indices():
+    """SB3: env_method("reset", indices=[...]) resets only those envs."""
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n = 64
+    env = BatchedChaosVecEnv("lorenz3", n, seed=2, max_episode_steps=50)
+    env.reset()
+    for _ in range(3):
+        env.step(np.zeros((n, 3), np.float32))
+    before = np.stack(env.get_attr("state1"))
+    lens = env.get_attr("current_step")
+    assert all(v == 3 for v in lens)
+    idx = [1, 7, 40]
+    out = env.env_method("reset", indices=idx)
+    assert len(out) == 3 and out[0][0].shape == (6,) and out[0][1] == {}
+    after = np.stack(env.get_attr("state1"))
+    lens = env.get_attr("current_step")
+    others = [i for i in range(n) if i not in idx]
+    assert np.array_equal(after[others], before[others]) and all(lens[i] == 3 for i in others)
+    assert all(lens[i] == 0 for i in idx) and not np.array_equal(after[idx], before[idx])
+    assert np.allclose(np.stack([o for o, _ in out])[:, :3], after[idx].astype(np.float32))
+    assert len(env.env_method("reset")) == n and all(v == 0 for v in env.get_attr("current_step"))
     env.close()
 
 
@@ -213,12 +272,14 @@ def test_graph_mode_replay_equals_eager_stepping(kind):
 
 @pytest.mark.parametrize("kind", ["lorenz_rk4", "hr_sync", "pmsm_sync"])
 def test_host_step_modes_give_identical_results(kind):
-    """DMA chain, zero-copy and the sliced two-stream pipeline are the same computation: every
+    """DMA chain, zero-copy, the sliced two-stream pipeline and the streamed mode (kernel launched before
+    the caller's array is staged, blocks wait for their slice's generation flag) are the same computation: every
     obs / reward / done / info must agree bit for bit, at a batch size that is not a multiple of
     the slice granularity and with episodes ending inside the window."""
     from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
     n, T = 20000 + 37, 9
-    modes = [("dma", 1), ("zerocopy", 1), ("pipelined", 2), ("pipelined", 3), ("pipelined", 7), ("pipelined", 64)]
+    modes = [("dma", 1), ("zerocopy", 1), ("pipelined", 2), ("pipelined", 3), ("pipelined", 7), ("pipelined", 64),
+             ("streamed", 1), ("streamed", 3), ("streamed", 16), ("streamed", 64)]
     rng = np.random.default_rng(5)
     ref = None
     for mode, k in modes:
@@ -249,3 +310,37 @@ def test_host_step_modes_give_identical_results(kind):
             assert len(trace) == len(ref)
             for k_, (x, y) in enumerate(zip(trace, ref)):
                 assert np.array_equal(np.asarray(x), np.asarray(y), equal_nan=True), (mode, k, k_)
+
+
+def test_tensor_path_has_no_host_round_trip():
+    """SURVEY 8d cfg 5: on the tensor / DLPack path observations and rewards reach the policy as device
+    tensors with NO host round trip.  64 policy -> step_tensor iterations under torch.profiler (CUPTI
+    activity records): the loop contains our step kernel 64 times and not a single host<->device memcpy."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
+    n = 4096
+    env = BatchedChaosVecEnv("hr_sync", n, seed=3)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.Tanh(), torch.nn.Linear(32, 2), torch.nn.Tanh()).to("cuda:0")
+    obs = env.reset_tensor()
+    with torch.no_grad():
+        for _ in range(4):                         # warm-up outside the profiled region
+            obs, rew, done = env.step_tensor(net(obs))
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            ret = torch.zeros(n, dtype=torch.float64, device="cuda:0")
+            for _ in range(64):
+                obs, rew, done = env.step_tensor(net(obs))
+                ret += rew
+            cap = torch.utils.dlpack.from_dlpack(env.obs_dlpack())     # the DLPack hand-off itself
+            torch.cuda.synchronize()
+    assert cap.data_ptr() == env.batch.obs_planes.data_ptr()
+    names = [e.name for e in prof.events()]
+    ours = [x for x in names if "k_step" in x]
+    if not ours:
+        pytest.skip("no CUDA activity records (CUPTI unavailable on this box)")
+    assert len(ours) == 64, len(ours)
+    copies = [x for x in names if "memcpy" in x.lower() and ("htod" in x.lower() or "dtoh" in x.lower())]
+    assert copies == [], copies
+    assert bool(torch.isfinite(ret).all())
+    env.close()

@@ -7,8 +7,10 @@ from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "lorenz_rk4"
 sizes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [4096, 16384, 65536, 262144]
-modes = [("dma", 1), ("zerocopy", 1), ("pipelined", 2), ("pipelined", 3), ("pipelined", 4), ("pipelined", 6),
-         ("pipelined", 8), ("pipelined", 16)]
+modes = [("dma", 1), ("zerocopy", 1), ("pipelined", 2), ("pipelined", 4), ("streamed", 1), ("streamed", 2),
+         ("streamed", 4), ("streamed", 8), ("streamed", 16)]
+if len(sys.argv) > 3:
+    modes = [(m.split(":")[0], int(m.split(":")[1])) for m in sys.argv[3].split(",")]
 for N in sizes:
     env = BatchedChaosVecEnv(kind, N)
     env.reset()
@@ -17,7 +19,7 @@ for N in sizes:
     acts = [rng.uniform(-1, 1, (N, b.act_dim)).astype(np.float32) for _ in range(4)]
     pin = b.host_action_buffer(); pin[:] = acts[0]
 
-    def bench(fn, n=400):
+    def bench(fn, n=300):
         for _ in range(30): fn(0)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         for k in range(n): fn(k)
