@@ -102,6 +102,10 @@ __device__ __forceinline__ double pow_pos(double x, double a) {
   // alpha = 1/2 is the envs' default exponent: a correctly rounded sqrt (~10 FP64 instructions
   // instead of ~150 for log + exp); warp-uniform test (a is a launch parameter).  x < 0 -> NaN, as pow.
   if (a == 0.5) return sqrt(x);
+  // alpha = 1/3 (the memristive pair's reward, lorenz_env_transient2.py): cbrt is ~4x cheaper than
+  // log + exp and within 1 ulp of pow(x, 0.3333333333333333) for every x the reward can reach
+  // (the exponent's rounding error shifts the result by ln(x) * 1.9e-17 relative)
+  if (a == 1.0 / 3) return cbrt(x);
   if (!(a > 0.0) || !(a < 64.0)) return pow(x, a);
   if (x == 0.0) return 0.0;
   return exp(a * log(x));   // log(inf)=inf -> inf, NaN propagates, x<0 -> NaN like pow for non-integer a
@@ -599,6 +603,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Every wait loop of the scheduling kernels is bounded: a protocol bug must end in a launch failure
+// (trap -> cudaErrorLaunchFailure at the next synchronisation), never in a kernel that spins forever.
+__device__ __forceinline__ void spin_guard(uint32_t& spins) {
+  if (++spins > (1u << 24)) __trap();
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -695,7 +704,8 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
       // The warp barrier extends the ordering from lane 0 to the other lanes; all per-env loads
       // additionally bypass L1.
       if (lane == 0) {
-        while (ld_acquire_u32(p.dyn_progress + e) < c) __nanosleep(32);
+        uint32_t spins = 0;
+        while (ld_acquire_u32(p.dyn_progress + e) < c) { __nanosleep(32); spin_guard(spins); }
       }
       __syncwarp();
     }
@@ -788,7 +798,7 @@ struct SmLayout {
     ep_ret = o; o += (size_t)cnt * 32 * sizeof(double);
     ep_len = o; o += (size_t)cnt * 32 * sizeof(int32_t);
     mbar = o;   o += (size_t)cnt * 3 * sizeof(uint64_t);                      // 2 action buffers + hand-off
-    prog = o;   o += sizeof(uint32_t);                                        // task counter
+    prog = o;   o += ((size_t)cnt + 1) * sizeof(uint32_t);                    // chunks finished per env-warp, task counter
     total = (o + 127) & ~(size_t)127;
   }
 };
@@ -828,12 +838,13 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   double* const s_ret = (double*)(sm_raw + L.ep_ret);
   int32_t* const s_len = (int32_t*)(sm_raw + L.ep_len);
   uint64_t* const mbar = (uint64_t*)(sm_raw + L.mbar);     // [le][0..1]: action buffers, [le][2]: hand-off
-  uint32_t* const counter = (uint32_t*)(sm_raw + L.prog);
+  volatile uint32_t* const prog = (volatile uint32_t*)(sm_raw + L.prog);
+  uint32_t* const counter = (uint32_t*)(sm_raw + L.prog) + cmax;
   const int per_buf = Tc * E::ACT * 32;  // floats
 
-  // ---- prologue: barriers, queue word, the block's state planes -> shared memory
+  // ---- prologue: barriers, queue words, the block's state planes -> shared memory
   for (int k = threadIdx.x; k < cnt * 3; k += blockDim.x) mbar_init(&mbar[k], 1);
-  if (threadIdx.x == 0) *counter = 0u;
+  for (int k = threadIdx.x; k <= cmax; k += blockDim.x) ((uint32_t*)(sm_raw + L.prog))[k] = 0u;
   for (int k = threadIdx.x; k < cnt * 32; k += blockDim.x) {
     const int le = k >> 5, ln = k & 31;
     const int64_t i = (int64_t)(e0 + le) * 32 + ln;   // < n_pad: the planes are padded
@@ -879,13 +890,22 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
     const bool live = i < p.n;
     if (c > 0) {
       // Hand-off: chunk c-1 of this env-warp was grabbed `cnt` grabs ago (c-major order) by another
-      // warp of this block and has practically always finished.  Its completion is phase c-1 of the
-      // env-warp's hand-off mbarrier (arrive = release, try_wait = acquire, both CTA scope): no
-      // MEMBAR -- a __threadfence_block() here also waits for the warp's outstanding global output
-      // stores, ~0.5 us per task.
+      // warp of this block and has practically always finished.  Two steps:
+      //  1. wait until exactly c chunks are counted in prog[le] (plain shared-memory word: a phase
+      //     PARITY alone cannot tell "chunk c-1 finished" from "chunk c-3 finished" when an SM owns
+      //     fewer env-warps than it has workers and several chunks of one env-warp are in hand);
+      //  2. the completion of chunk c-1 is phase c-1 of the env-warp's hand-off mbarrier, whose arrive
+      //     follows the counter store: try_wait on that phase is the acquire (arrive = release, CTA
+      //     scope) that orders the state loads below.  No MEMBAR -- a __threadfence_block() here also
+      //     waits for the warp's outstanding global output stores, ~0.5 us per task.
+      uint32_t spins = 0;
+      if (lane == 0) {
+        while (prog[le] != (uint32_t)c) { __nanosleep(32); spin_guard(spins); }
+      }
+      __syncwarp();
       uint64_t* hb = &mbar[le * 3 + 2];
       const uint32_t parity = (uint32_t)(c - 1) & 1u;
-      while (!mbar_try_wait(hb, parity)) __nanosleep(32);
+      while (!mbar_try_wait(hb, parity)) spin_guard(spins);
     }
     if (c + 1 < nchunks) {
       // Buffer (c+1)&1 was last READ (LDS, generic proxy) during chunk c-1; those loads had returned
@@ -903,7 +923,8 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
     {
       uint64_t* bar = &mbar[le * 3 + (c & 1)];
       const uint32_t parity = (uint32_t)(c >> 1) & 1u;
-      while (!mbar_try_wait(bar, parity)) {}
+      uint32_t spins = 0;
+      while (!mbar_try_wait(bar, parity)) spin_guard(spins);
     }
     const float* ab = act + (size_t)(le * 2 + (c & 1)) * per_buf;
     bool fin = E::finite(s);
@@ -926,9 +947,13 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
     E::store_sm(s, st + (size_t)le * E::NSTATE * 32, lane);
     s_len[le * 32 + lane] = ep_len;
     s_ret[le * 32 + lane] = ep_ret;
-    // publish: the warp barrier orders every lane's shared-memory stores before lane 0's arrive
+    // publish: the warp barrier orders every lane's shared-memory stores before lane 0's counter
+    // store and arrive (release)
     __syncwarp();
-    if (lane == 0) mbar_arrive(&mbar[le * 3 + 2]);
+    if (lane == 0) {
+      prog[le] = (uint32_t)c + 1u;
+      mbar_arrive(&mbar[le * 3 + 2]);
+    }
     if (CL_PLAIN_DEFER) plain_emit<E, true>(p, i, live, pend);   // the last interval's outputs, after the hand-off
     q = grab();
   }

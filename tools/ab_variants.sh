@@ -9,7 +9,7 @@ for spec in "$@"; do
   lib=build/variants/lib_$name.so
   [[ "$name" == main ]] && lib=gym_lorenz_b200/libchaos_b200.so
   for rep in 1 2; do
-    line=$(env CHAOS_B200_LIB=$lib $envs python bench.py --steps 300 --warmup 5 --no-e2e --no-cpu-baseline ${BENCH_ARGS} 2>/dev/null | tail -1)
+    line=$(env CHAOS_B200_LIB=$lib $envs timeout -k 5 300 python bench.py --steps 300 --warmup 5 --no-e2e --no-cpu-baseline ${BENCH_ARGS} 2>/dev/null | tail -1)
     echo "{\"variant\": \"$spec\", \"rep\": $rep, \"line\": $line}" >> $out
   done
 done
