@@ -409,7 +409,7 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
           int workers = 4 * ((cmax + 3) / 4);
           workers = workers > 12 ? 12 : workers;
           if (const char* w = getenv("CHAOS_B200_SM_WORKERS")) { const int k = atoi(w); if (k >= 1 && k <= 16) workers = k; }
-          int sc = 4;
+          int sc = 8;
           if (const char* w = getenv("CHAOS_B200_SM_CHUNK")) { const int k = atoi(w); if (k >= 1 && k <= 16) sc = k; }
           if (cmax <= 64) { p.sm_grid = grid; p.sm_workers = workers; p.sm_chunk = sc; }
         }
@@ -617,6 +617,7 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
     if (h.gen == 0) h.gen = 1;
     *h.h_err = 0u;
     p.act_ready = h.h_ready; p.act_gen = h.gen; p.act_slice_envs = (int32_t)per; p.host_err = h.h_err;
+    { const char* ov = getenv("CHAOS_B200_POLL"); p.act_poll = (ov && ov[0] == '1') ? 1 : 0; }
     r = launch(ctx, p, cl::MODE_STEP, st);
     if (r) return r;
     int j = 0;

@@ -49,6 +49,7 @@ struct KParams {
   int32_t host_rows;
   const uint32_t* act_ready;
   uint32_t act_gen;
+  int32_t act_poll;        // 0: relaxed volatile polling (default), 1: ld.acquire.sys (A/B only)
   int32_t act_slice_envs;
   uint32_t* host_err;
   // rollout
@@ -507,13 +508,20 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
     // that word over PCIe, the state loads above are already in flight meanwhile.  Bounded wait: after
     // ~2 s the block gives up, flags the error for cl_step_host_wait and proceeds.
     if (threadIdx.x == 0) {
-      const uint32_t* flag = p.act_ready + (i - p.i_begin) / p.act_slice_envs;
+      // Relaxed (volatile) polling: an acquire at SYSTEM scope costs a MEMBAR.SYS per poll -- measured
+      // ~4.5 us each and serialised across the grid (1 ms per step at 256 blocks).  Ordering of the action
+      // loads behind the flag: they are volatile loads issued after the branch on the flag value resolved
+      // (no speculation past it), and the CPU publishes with a release store after writing the slice.
+      const volatile uint32_t* flag = p.act_ready + (i - p.i_begin) / p.act_slice_envs;
       uint64_t t0 = 0, t1 = 0;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-      while (ld_acquire_sys_u32(flag) != p.act_gen) {
-        __nanosleep(200);
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 2000000000ull) { if (p.host_err) *p.host_err = 1u; break; }
+      uint32_t polls = 0;
+      while ((p.act_poll == 1 ? ld_acquire_sys_u32((const uint32_t*)flag) : *flag) != p.act_gen) {
+        __nanosleep(100);
+        if ((++polls & 63u) == 0u) {
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t0 == 0) t0 = t1;
+          if (t1 - t0 > 2000000000ull) { if (p.host_err) *p.host_err = 1u; break; }
+        }
       }
     }
     __syncthreads();
@@ -824,14 +832,20 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   const int e0 = b * qn + (b < rn ? b : rn);
   const int cnt = qn + (b < rn ? 1 : 0);
   const int cmax = qn + (rn ? 1 : 0);
-  // Task schedule of one env-warp: full chunks of Tc control intervals, then -- so that the last round
-  // of tasks, in which workers run dry, is short -- the final two chunks' worth in pieces of Tc / 4.
-  const int Tc = p.sm_chunk, Ts = Tc >= 4 ? Tc / 4 : 1;
-  const int n_full = p.T > 2 * Tc ? (p.T - 2 * Tc) / Tc : 0;
-  const int t_tail = n_full * Tc;
-  const int nchunks = n_full + (p.T - t_tail + Ts - 1) / Ts;
-  auto chunk_t0 = [&](int c) { return c < n_full ? c * Tc : t_tail + (c - n_full) * Ts; };
-  auto chunk_len = [&](int c) { return c < n_full ? Tc : min(Ts, p.T - (t_tail + (c - n_full) * Ts)); };
+  // Task schedule of local env-warp le: a first chunk of f(le) = 1 + le * Tc / cnt control intervals,
+  // then chunks of Tc.  The staggered first chunk spreads the task boundaries of an SM's env-warps over
+  // time: with identical boundaries all worker warps of a scheduler reach their task switch (queue
+  // atomic, hand-off wait, state and action loads: several hundred cycles of latency, no FP64 issue)
+  // at the same moment and nobody covers for anybody -- measured 0.5 us lost per task.  It also gives
+  // the last round of tasks mixed lengths 1..Tc, which shortens the tail.  Every env-warp has the same
+  // number of chunks (c-major queue); trailing chunks past T are empty.
+  const int Tc = p.sm_chunk;
+  const int nchunks = 1 + (p.T - 1 + Tc - 1) / Tc;
+  auto chunk_t0 = [&](int le, int c) { return c == 0 ? 0 : min(p.T, 1 + le * Tc / cnt + (c - 1) * Tc); };
+  auto chunk_len = [&](int le, int c) {
+    const int t0 = chunk_t0(le, c);
+    return min(c == 0 ? 1 + le * Tc / cnt : Tc, p.T - t0);
+  };
   const SmLayout<E> L(cmax, Tc);
   float* const act = (float*)(sm_raw + L.act);
   real* const st = (real*)(sm_raw + L.state);
@@ -859,8 +873,8 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   // stage the actions of chunk c of local env-warp le into its buffer (c & 1): lanes 0..len*ACT-1
   // issue one 128 B copy each, completion counted on the buffer's mbarrier
   auto stage = [&](int le, int c) {
-    const int t0 = chunk_t0(c);
-    const int len = chunk_len(c);
+    const int t0 = chunk_t0(le, c);
+    const int len = chunk_len(le, c);
     uint64_t* bar = &mbar[le * 3 + (c & 1)];
     float* dst = act + (size_t)(le * 2 + (c & 1)) * per_buf;
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)(len * E::ACT * 128));
@@ -884,8 +898,8 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   uint32_t q = grab();
   while (q < total) {
     const int le = (int)(q % (uint32_t)cnt), c = (int)(q / (uint32_t)cnt);
-    const int t0 = chunk_t0(c);
-    const int len = chunk_len(c);
+    const int t0 = chunk_t0(le, c);
+    const int len = chunk_len(le, c);
     const int64_t i = (int64_t)(e0 + le) * 32 + lane;
     const bool live = i < p.n;
     if (c > 0) {
