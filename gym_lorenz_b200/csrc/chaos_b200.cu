@@ -340,6 +340,34 @@ extern "C" int cl_step(cl_ctx* ctx, void* stream, const cl_buffers* buf, const c
   return r;
 }
 
+// Tensor map of a rollout's action tensor, f32 [T][A][row stride] with env stride 1: dims (x = envs,
+// y = channels, z = intervals), box (32, A, chunk) = what one env-warp consumes in one chunk, fetched by
+// k_rollout_sm with one cp.async.bulk.tensor per chunk.  The encoder is a driver entry point, looked up
+// through the runtime (no link-time dependency on libcuda).  false -> the kernel copies row by row.
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool action_tensor_map(CUtensorMap* out, const float* base, uint64_t n_x, uint64_t n_ch, uint64_t T,
+                              uint64_t row_stride, uint64_t t_stride, uint32_t chunk) {
+  static encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_fn)f;
+  }
+  if (!fn || chunk < 1 || chunk > 256 || n_ch > 256 || T < chunk) return false;
+  const cuuint64_t dims[3] = {n_x, n_ch, T};
+  const cuuint64_t strides[2] = {row_stride * sizeof(float), t_stride * sizeof(float)};   // of dims 1, 2 (bytes)
+  const cuuint32_t box[3] = {32, (cuuint32_t)n_ch, chunk};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Dynamic (env-warp x interval-chunk) scheduling pays off when the env-warps do not divide
 // evenly over the 4 x SMs warp schedulers; CHAOS_B200_DYN=0/1 forces it off/on.
 static bool want_dynamic(const cl_ctx* ctx, int T, int chunk) {
@@ -399,19 +427,28 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
       p.dyn_tma = (io->action != nullptr && io->act_es == 1 && (io->act_cs % 4) == 0 && (d->act_ts % 4) == 0 &&
                    ((uintptr_t)io->action % 16) == 0 && io->act_cs >= W * 32) ? 1 : 0;
       // SM-local variant (k_rollout_sm, plain rollout shape only -- launch_env decides): one block per
-      // SM owning W / SMs env-warps; 3 worker warps per scheduler unless the SM owns fewer env-warps.
+      // SM owning W / SMs env-warps.  Workers = resident env-warps per block: a multiple of 4 (one per
+      // scheduler and round) not above the smallest per-SM env-warp count, at most 16; the rest are guests.
       // CHAOS_B200_SM=0 keeps the global queue; CHAOS_B200_SM_WORKERS / _SM_CHUNK override (tuning).
       {
         const char* ov = getenv("CHAOS_B200_SM");
         if (!(ov && ov[0] == '0') && p.dyn_tma) {
           const int grid = (int)(W < ctx->sm_count ? W : ctx->sm_count);
-          const int cmax = (int)((W + grid - 1) / grid);
-          int workers = 4 * ((cmax + 3) / 4);
-          workers = workers > 12 ? 12 : workers;
-          if (const char* w = getenv("CHAOS_B200_SM_WORKERS")) { const int k = atoi(w); if (k >= 1 && k <= 16) workers = k; }
+          const int qn = (int)(W / grid), cmax = (int)((W + grid - 1) / grid);
+          int workers = qn >= 4 ? 4 * (qn / 4) : qn;
+          workers = workers > 16 ? 16 : workers;
+          if (workers == 16 && qn < 20) workers = 12;   // 16..19 env-warps: 12 residents + 4..7 guests balance better than 16 + 0..3
+          if (const char* w = getenv("CHAOS_B200_SM_WORKERS")) { const int k = atoi(w); if (k >= 1 && k <= 16) workers = k < qn ? k : qn; }
           int sc = 8;
           if (const char* w = getenv("CHAOS_B200_SM_CHUNK")) { const int k = atoi(w); if (k >= 1 && k <= 16) sc = k; }
-          if (cmax <= 64) { p.sm_grid = grid; p.sm_workers = workers; p.sm_chunk = sc; }
+          if (sc > d->T) sc = d->T;
+          if (cmax <= 64) {
+            p.sm_grid = grid; p.sm_workers = workers; p.sm_chunk = sc;
+            p.sm_tmap_ok = action_tensor_map(&p.sm_tmap, io->action, (uint64_t)W * 32, (uint64_t)ctx->lay.act_dim,
+                                             (uint64_t)d->T, (uint64_t)io->act_cs, (uint64_t)d->act_ts, (uint32_t)sc) ? 1 : 0;
+            const char* tm = getenv("CHAOS_B200_SM_TMAP");
+            if (tm && tm[0] == '0') p.sm_tmap_ok = 0;
+          }
         }
       }
       mode = cl::MODE_ROLLOUT_DYN;

@@ -7,6 +7,7 @@
 // accounting and warp-reduced statistics.  State stays in registers across all T control
 // intervals (and all RK4 substeps) of a launch.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -77,6 +78,8 @@ struct KParams {
   int32_t dyn_chunk, dyn_nchunks, dyn_nwarps, dyn_tma, dyn_grid;
   // SM-local rollout scheduling (k_rollout_sm): grid, worker warps per block, control intervals per task
   int32_t sm_grid, sm_workers, sm_chunk;
+  int32_t sm_tmap_ok;                  // sm_tmap describes the action tensor (x env, y channel, z interval)
+  alignas(64) CUtensorMap sm_tmap;
   // observations go out as contiguous, 16-byte aligned float32 rows -> warp-transposed vector stores
   int32_t rows_fast;
   int32_t no_plain;  // host-side only: keep the generic instantiation (tests, A/B runs)
@@ -508,10 +511,9 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
     // that word over PCIe, the state loads above are already in flight meanwhile.  Bounded wait: after
     // ~2 s the block gives up, flags the error for cl_step_host_wait and proceeds.
     if (threadIdx.x == 0) {
-      // Relaxed (volatile) polling: an acquire at SYSTEM scope costs a MEMBAR.SYS per poll -- measured
-      // ~4.5 us each and serialised across the grid (1 ms per step at 256 blocks).  Ordering of the action
-      // loads behind the flag: they are volatile loads issued after the branch on the flag value resolved
-      // (no speculation past it), and the CPU publishes with a release store after writing the slice.
+      // Relaxed (volatile) polling, no system-scope fence per poll.  Ordering of the action loads behind
+      // the flag: they are issued after the branch on the flag value resolved (no speculation past it) and
+      // after the block barrier below; the CPU publishes with a release store after writing the slice.
       const volatile uint32_t* flag = p.act_ready + (i - p.i_begin) / p.act_slice_envs;
       uint64_t t0 = 0, t1 = 0;
       uint32_t polls = 0;
@@ -532,10 +534,12 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
   // the dynamic kernel below stages them through shared memory instead
   float a_next[E::ACT];
 #pragma unroll
-  for (int c = 0; c < E::ACT; ++c) {
-    if (streamed) a_next[c] = live ? __ldcv(p.action + i * p.act_es + c * p.act_cs) : 0.0f;   // written by the CPU during this launch
-    else a_next[c] = (live && (PLAIN || p.action != nullptr)) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
-  }
+  // Streamed mode: ordinary (L1-allocating) loads on purpose.  The rows of this block are whole 128-byte
+  // lines nobody touched before the flag above was seen (L1 is invalidated at launch), so they are fetched
+  // fresh; volatile loads instead re-fetch every 32-byte sector over PCIe for each of the ACT strided
+  // loads of a row -- measured 1 ms per step at 65,536 envs (request-rate bound).
+  for (int c = 0; c < E::ACT; ++c)
+    a_next[c] = (live && (PLAIN || p.action != nullptr)) ? p.action[i * p.act_es + c * p.act_cs] : 0.0f;
 
   unsigned bad_acc = 0u;
   bool fin = E::finite(s);
@@ -781,18 +785,26 @@ __global__ void __launch_bounds__(128) k_rollout_dyn(const KParams p) {
 
 
 // ---- the SM-local rollout kernel ----------------------------------------------------------
-// Same idea as k_rollout_dyn (env-warp x interval-chunk tasks pulled by persistent worker warps, so
-// that 2048 env-warps spread evenly over 592 schedulers), but the queue is PER SM: block b (one per
-// SM, 120 KB of shared memory so that no two share an SM) owns a contiguous range of 13-14 env-warps
-// for the whole launch.  Their state, episode counters and staged actions live in shared memory; the
-// task counter and the per-env-warp progress words are shared-memory words.  A task hand-off is a
-// few LDS/STS and a block-scope fence instead of a GPU-scope release/acquire through L2 -- in
-// k_rollout_dyn the acquire's L1 invalidate (CCTL.IVALL), the release's ERRBAR and the cold state
-// loads were ~11 % of all stall samples (profiles/r01f_dyn_ncu_full_metrics.txt) -- so tasks can be
-// short (4 intervals: the last round of tasks is 99.6 % full) and no SM waits for another one.
+// Same goal as k_rollout_dyn -- 2048 env-warps spread evenly over 592 schedulers -- but nothing crosses
+// an SM.  Block b (one per SM: >= 120 KB of shared memory each keeps two blocks off one SM) owns a
+// contiguous range of 13-14 env-warps for the whole launch:
+//  * RESIDENTS: worker warp w integrates env-warp w from the first to the last control interval with
+//    its state in registers -- no task switch, no hand-off; 12 workers = 3 per scheduler.
+//  * GUESTS: the 1-2 env-warps an SM owns beyond its workers are cut into chunks of Tc intervals; their
+//    state, episode counters and hand-off words live in shared memory.  After every nres / g of its own
+//    chunks (Bresenham, phase-shifted per worker) a worker parks its resident in shared memory, runs ONE
+//    guest chunk and resumes -- so every worker does (1 + g / nres) x T intervals and all finish
+//    together, with ~7x fewer task switches than a queue holding every env-warp (that version spent
+//    ~9 % of its stall samples in per-task code: queue atomic, index arithmetic, hand-off wait, state and
+//    pointer set-up, a 23-iteration uniform loop issuing the chunk's bulk copies).
+//  * A guest hand-off is shared-memory only: chunk counter + mbarrier (arrive = release, try_wait =
+//    acquire, CTA scope) -- no GPU-scope release/acquire through L2 as in k_rollout_dyn (CCTL.IVALL,
+//    ERRBAR and cold state loads: ~11 % of its stall samples), and no MEMBAR at all.
+//  * ACTIONS: per env-warp double buffer in shared memory; a chunk [Tc][ACT][32] f32 arrives by ONE
+//    3-D tensor copy (cp.async.bulk.tensor, completion on the buffer's mbarrier) issued by one lane a
+//    whole chunk ahead; rows past T are zero-filled by the copy engine.  Without a tensor map (driver
+//    entry point missing) the chunk is fetched by one 128 B bulk copy per row.
 // Cost: SMs owning 14 env-warps run 1.2 % longer than the 13.84 average.
-// Actions: per env-warp double buffer in shared memory, filled by bulk async copies (mbarrier
-// completion) issued one whole task ahead by whichever warp runs the preceding chunk.
 // Plain rollout I/O shape only (PlainRollout<E>): launch_env falls back to k_rollout_dyn otherwise.
 
 template <class E>
@@ -806,46 +818,49 @@ struct SmLayout {
     ep_ret = o; o += (size_t)cnt * 32 * sizeof(double);
     ep_len = o; o += (size_t)cnt * 32 * sizeof(int32_t);
     mbar = o;   o += (size_t)cnt * 3 * sizeof(uint64_t);                      // 2 action buffers + hand-off
-    prog = o;   o += ((size_t)cnt + 1) * sizeof(uint32_t);                    // chunks finished per env-warp, task counter
+    prog = o;   o += ((size_t)cnt + 1) * sizeof(uint32_t);                    // chunks finished per env-warp, guest queue
     total = (o + 127) & ~(size_t)127;
   }
 };
 
-template <class E>
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int x, int y, int z, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+      : "memory");
+}
+
 #ifndef CL_SM_THREADS
-#define CL_SM_THREADS 512
+#define CL_SM_THREADS 576
 #endif
 #ifndef CL_SM_MINB
 #define CL_SM_MINB 0
 #endif
-// (512, no minimum-blocks hint): with this bound ptxas keeps the two x-multiplied DFMAs of every RHS
-// evaluation adjacent, so the second one finds x in the operand reuse cache (2.2 instead of 3 issue
-// cycles); (512, 1) and (384, 1) schedule them apart -- checked on the built library by
-// tests/test_sass.py with tools/sass_mix.py
-__global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const KParams p) {
+// Launch bound (576, no minimum-blocks hint; blocks have at most 16 warps): a ptxas scheduling lottery.
+// With this bound (92 registers) the two x-multiplied DFMAs of every RHS evaluation end up adjacent, so
+// 106 of the 128 three-register DFMAs of an interval find one source in the operand reuse cache (2.2
+// instead of 3 issue cycles, tools/dfma_probe.cu); (512, 0) gives 1 of 128, (384, 0) 76 of 128 --
+// checked on the built library by tests/test_sass.py with tools/sass_mix.py
+template <class E>
+__global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const __grid_constant__ KParams p) {
   typedef typename E::real real;
   extern __shared__ __align__(128) unsigned char sm_raw[];
   const unsigned lane = threadIdx.x & 31u;
-  const int wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int wib = threadIdx.x >> 5, nres = blockDim.x >> 5;     // one resident env-warp per worker warp
   const int W = p.dyn_nwarps, G = (int)gridDim.x, b = (int)blockIdx.x;
   const int qn = W / G, rn = W % G;
   const int e0 = b * qn + (b < rn ? b : rn);
-  const int cnt = qn + (b < rn ? 1 : 0);
+  const int cnt = qn + (b < rn ? 1 : 0);                       // >= nres by construction (host)
   const int cmax = qn + (rn ? 1 : 0);
-  // Task schedule of local env-warp le: a first chunk of f(le) = 1 + le * Tc / cnt control intervals,
-  // then chunks of Tc.  The staggered first chunk spreads the task boundaries of an SM's env-warps over
-  // time: with identical boundaries all worker warps of a scheduler reach their task switch (queue
-  // atomic, hand-off wait, state and action loads: several hundred cycles of latency, no FP64 issue)
-  // at the same moment and nobody covers for anybody -- measured 0.5 us lost per task.  It also gives
-  // the last round of tasks mixed lengths 1..Tc, which shortens the tail.  Every env-warp has the same
-  // number of chunks (c-major queue); trailing chunks past T are empty.
+  const int ng = cnt - nres;                                   // guests of this block
+  // Chunk schedule of local env-warp le: a first chunk of f(le) = 1 + le * Tc / cnt control intervals,
+  // then chunks of Tc: chunk boundaries (action-buffer swaps, guest slots) of the warps sharing a
+  // scheduler do not coincide, and the guests' last chunks have mixed lengths.  Every env-warp has the
+  // same number of chunks; trailing chunks past T are empty.
   const int Tc = p.sm_chunk;
   const int nchunks = 1 + (p.T - 1 + Tc - 1) / Tc;
-  auto chunk_t0 = [&](int le, int c) { return c == 0 ? 0 : min(p.T, 1 + le * Tc / cnt + (c - 1) * Tc); };
-  auto chunk_len = [&](int le, int c) {
-    const int t0 = chunk_t0(le, c);
-    return min(c == 0 ? 1 + le * Tc / cnt : Tc, p.T - t0);
-  };
+  auto chunk_t0 = [&](int f, int c) { return c == 0 ? 0 : min(p.T, f + (c - 1) * Tc); };
+  auto chunk_len = [&](int f, int c) { return min(c == 0 ? f : Tc, p.T - chunk_t0(f, c)); };
   const SmLayout<E> L(cmax, Tc);
   float* const act = (float*)(sm_raw + L.act);
   real* const st = (real*)(sm_raw + L.state);
@@ -870,80 +885,45 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  // stage the actions of chunk c of local env-warp le into its buffer (c & 1): lanes 0..len*ACT-1
-  // issue one 128 B copy each, completion counted on the buffer's mbarrier
-  auto stage = [&](int le, int c) {
-    const int t0 = chunk_t0(le, c);
-    const int len = chunk_len(le, c);
+  // stage the actions of chunk c of local env-warp le into its buffer (c & 1)
+  auto stage = [&](int le, int f, int c) {
+    const int t0 = chunk_t0(f, c);
     uint64_t* bar = &mbar[le * 3 + (c & 1)];
     float* dst = act + (size_t)(le * 2 + (c & 1)) * per_buf;
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(len * E::ACT * 128));
-    __syncwarp();
-    for (int k = (int)lane; k < len * E::ACT; k += 32) {  // every expected byte must be issued
-      const int tl = k / E::ACT, cc = k % E::ACT;
-      const float* src = p.action + (int64_t)(t0 + tl) * p.act_ts + (int64_t)cc * p.act_cs + (int64_t)(e0 + le) * 32;
-      bulk_g2s(dst + (tl * E::ACT + cc) * 32, src, 128u, bar);
+    if (p.sm_tmap_ok) {
+      // one tensor copy: box (32 envs, ACT channels, Tc intervals); the whole box counts towards the
+      // barrier's transaction bytes, rows past T arrive as zeros
+      if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(per_buf * sizeof(float)));
+        tma_load_3d(dst, &p.sm_tmap, (e0 + le) * 32, 0, t0, bar);
+      }
+    } else {
+      const int len = chunk_len(f, c);
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(len * E::ACT * 128));
+      __syncwarp();
+      for (int k = (int)lane; k < len * E::ACT; k += 32) {  // every expected byte must be issued
+        const int tl = k / E::ACT, cc = k % E::ACT;
+        const float* src = p.action + (int64_t)(t0 + tl) * p.act_ts + (int64_t)cc * p.act_cs + (int64_t)(e0 + le) * 32;
+        bulk_g2s(dst + (tl * E::ACT + cc) * 32, src, 128u, bar);
+      }
     }
   };
-  for (int le = wib; le < cnt; le += nw) stage(le, 0);
+  auto wait_actions = [&](int le, int c) {
+    uint64_t* bar = &mbar[le * 3 + (c & 1)];
+    const uint32_t parity = (uint32_t)(c >> 1) & 1u;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) spin_guard(spins);
+  };
+  for (int le = wib; le < cnt; le += nres) stage(le, 1 + le * Tc / cnt, 0);
 
   const uint64_t step0 = step_base(p);
-  const uint32_t total = (uint32_t)cnt * (uint32_t)nchunks;
   unsigned bad_acc = 0u;
-  auto grab = [&]() -> uint32_t {
-    uint32_t q = 0;
-    if (lane == 0) q = atomicAdd(counter, 1u);
-    return __shfl_sync(0xffffffffu, q, 0);
-  };
-  uint32_t q = grab();
-  while (q < total) {
-    const int le = (int)(q % (uint32_t)cnt), c = (int)(q / (uint32_t)cnt);
-    const int t0 = chunk_t0(le, c);
-    const int len = chunk_len(le, c);
-    const int64_t i = (int64_t)(e0 + le) * 32 + lane;
-    const bool live = i < p.n;
-    if (c > 0) {
-      // Hand-off: chunk c-1 of this env-warp was grabbed `cnt` grabs ago (c-major order) by another
-      // warp of this block and has practically always finished.  Two steps:
-      //  1. wait until exactly c chunks are counted in prog[le] (plain shared-memory word: a phase
-      //     PARITY alone cannot tell "chunk c-1 finished" from "chunk c-3 finished" when an SM owns
-      //     fewer env-warps than it has workers and several chunks of one env-warp are in hand);
-      //  2. the completion of chunk c-1 is phase c-1 of the env-warp's hand-off mbarrier, whose arrive
-      //     follows the counter store: try_wait on that phase is the acquire (arrive = release, CTA
-      //     scope) that orders the state loads below.  No MEMBAR -- a __threadfence_block() here also
-      //     waits for the warp's outstanding global output stores, ~0.5 us per task.
-      uint32_t spins = 0;
-      if (lane == 0) {
-        while (prog[le] != (uint32_t)c) { __nanosleep(32); spin_guard(spins); }
-      }
-      __syncwarp();
-      uint64_t* hb = &mbar[le * 3 + 2];
-      const uint32_t parity = (uint32_t)(c - 1) & 1u;
-      while (!mbar_try_wait(hb, parity)) spin_guard(spins);
-    }
-    if (c + 1 < nchunks) {
-      // Buffer (c+1)&1 was last READ (LDS, generic proxy) during chunk c-1; those loads had returned
-      // their values before that chunk's warp arrived on the hand-off barrier we just waited on, so
-      // the bulk copy (async proxy) cannot overtake them.  No fence.proxy.async here -- it compiles to
-      // MEMBAR.ALL.CTA, which also waits for this warp's outstanding global output stores; the
-      // write-after-read direction is ordered by the mbarrier alone (the usual TMA pipeline pattern).
-      stage(le, c + 1);
-    }
-    typename E::S s = {};
-    E::load_sm(s, st + (size_t)le * E::NSTATE * 32, lane);
-    int32_t ep_len = s_len[le * 32 + lane];
-    double ep_ret = s_ret[le * 32 + lane];
-    E::prepare(s, p, live);
-    {
-      uint64_t* bar = &mbar[le * 3 + (c & 1)];
-      const uint32_t parity = (uint32_t)(c >> 1) & 1u;
-      uint32_t spins = 0;
-      while (!mbar_try_wait(bar, parity)) spin_guard(spins);
-    }
+
+  // the control intervals of one chunk of one env-warp; state, episode counters and the pending output
+  // record stay in the caller's registers
+  auto run_chunk = [&](typename E::S& s, int32_t& ep_len, double& ep_ret, bool& fin, PlainPending<E>& pend,
+                       const int le, const int c, const int t0, const int len, const int64_t i, const bool live) {
     const float* ab = act + (size_t)(le * 2 + (c & 1)) * per_buf;
-    bool fin = E::finite(s);
-    PlainPending<E> pend;
-    pend.begin(p, i, t0);
     auto intervals = [&](auto spec_tag) {
       constexpr int SPEC = decltype(spec_tag)::value;
       for (int tl = 0; tl < len; ++tl) {
@@ -958,18 +938,106 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
     };
     if (E::spec(s, p) == 1) intervals(SpecTag<1>{});
     else intervals(SpecTag<0>{});
-    E::store_sm(s, st + (size_t)le * E::NSTATE * 32, lane);
-    s_len[le * 32 + lane] = ep_len;
-    s_ret[le * 32 + lane] = ep_ret;
-    // publish: the warp barrier orders every lane's shared-memory stores before lane 0's counter
-    // store and arrive (release)
-    __syncwarp();
-    if (lane == 0) {
-      prog[le] = (uint32_t)c + 1u;
-      mbar_arrive(&mbar[le * 3 + 2]);
+  };
+
+  // ---- worker loop: own chunks in order, a guest chunk whenever the Bresenham credit says so.
+  // ONE call site of run_chunk (the unrolled interval body is ~13 KB of code per specialisation; a second
+  // inlined copy would double the instruction-cache footprint of the hot loop).
+  const uint32_t g_total = (uint32_t)ng * (uint32_t)nchunks;
+  typename E::S s = {};
+  int32_t ep_len = 0;
+  double ep_ret = 0.0;
+  bool fin = true;
+  PlainPending<E> pend;
+  pend.valid = 0u;
+  int in_regs = -1;                     // local env-warp whose state is in this warp's registers
+  int c_own = 0;
+  int credit = (wib * ng) % nres;       // phase shift: the workers' guest slots interleave evenly in time
+  bool guests_left = ng > 0, want_guest = false;
+  for (;;) {
+    int le, c;
+    bool guest;
+    if (want_guest) {
+      uint32_t q = 0;
+      if (lane == 0) q = atomicAdd(counter, 1u);
+      q = __shfl_sync(0xffffffffu, q, 0);
+      if (q >= g_total) { guests_left = false; want_guest = false; continue; }
+      guest = true; le = nres + (int)(q % (uint32_t)ng); c = (int)(q / (uint32_t)ng);
+    } else if (c_own < nchunks) {
+      guest = false; le = wib; c = c_own;
+    } else if (guests_left) {
+      want_guest = true;                // own env-warp finished: drain what is left of the guests
+      continue;
+    } else {
+      break;
     }
-    if (CL_PLAIN_DEFER) plain_emit<E, true>(p, i, live, pend);   // the last interval's outputs, after the hand-off
-    q = grab();
+    const int f = 1 + le * Tc / cnt;
+    const int t0 = chunk_t0(f, c), len = chunk_len(f, c);
+    const int64_t i = (int64_t)(e0 + le) * 32 + lane;
+    const bool live = i < p.n;
+    if (guest && c > 0) {
+      // Hand-off from the warp that ran chunk c-1 of this guest.  Two steps:
+      //  1. wait until exactly c chunks are counted in prog[le] (plain shared-memory word: a phase
+      //     PARITY alone cannot tell "chunk c-1 finished" from "chunk c-3 finished" when several
+      //     chunks of one env-warp are in hand);
+      //  2. the completion of chunk c-1 is phase c-1 of the env-warp's hand-off mbarrier, whose arrive
+      //     follows the counter store: try_wait on that phase is the acquire (arrive = release, CTA
+      //     scope) that orders the state loads below.  No MEMBAR -- a __threadfence_block() here also
+      //     waits for the warp's outstanding global output stores, ~0.5 us per task.
+      uint32_t spins = 0;
+      if (lane == 0) {
+        while (prog[le] != (uint32_t)c) { __nanosleep(32); spin_guard(spins); }
+      }
+      __syncwarp();
+      uint64_t* hb = &mbar[le * 3 + 2];
+      const uint32_t parity = (uint32_t)(c - 1) & 1u;
+      while (!mbar_try_wait(hb, parity)) spin_guard(spins);
+    }
+    // Buffer (c+1)&1 was last READ (LDS, generic proxy) during chunk c-1 -- by this warp (resident) or by
+    // the warp whose hand-off we just acquired (guest); those loads had returned their values long
+    // before.  No fence.proxy.async here -- it compiles to MEMBAR.ALL.CTA, which also waits for this
+    // warp's outstanding global output stores; the write-after-read direction is ordered by the mbarrier
+    // alone (the usual TMA pipeline pattern).
+    if (c + 1 < nchunks) stage(le, f, c + 1);
+    if (in_regs != le) {
+      E::load_sm(s, st + (size_t)le * E::NSTATE * 32, lane);
+      ep_len = s_len[le * 32 + lane];
+      ep_ret = s_ret[le * 32 + lane];
+      E::prepare(s, p, live);
+      fin = E::finite(s);
+      pend.begin(p, i, t0);
+      in_regs = le;
+    }
+    wait_actions(le, c);
+    run_chunk(s, ep_len, ep_ret, fin, pend, le, c, t0, len, i, live);
+    bool park;
+    if (guest) {
+      park = true;
+      want_guest = false;               // one guest chunk per slot
+    } else {
+      c_own += 1;
+      credit += ng;
+      want_guest = guests_left && credit >= nres && c_own < nchunks;
+      if (want_guest) credit -= nres;
+      park = want_guest || c_own == nchunks;
+    }
+    if (park) {
+      // state back to its shared-memory slot; a guest is then published to whichever warp runs its next
+      // chunk (the warp barrier orders every lane's stores before lane 0's counter store and arrive)
+      E::store_sm(s, st + (size_t)le * E::NSTATE * 32, lane);
+      s_len[le * 32 + lane] = ep_len;
+      s_ret[le * 32 + lane] = ep_ret;
+      if (guest) {
+        __syncwarp();
+        if (lane == 0) {
+          prog[le] = (uint32_t)c + 1u;
+          mbar_arrive(&mbar[le * 3 + 2]);
+        }
+      }
+      if (CL_PLAIN_DEFER) plain_emit<E, true>(p, i, live, pend);   // the last interval's outputs, after the hand-off
+      pend.valid = 0u;
+      in_regs = -1;
+    }
   }
   if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
 

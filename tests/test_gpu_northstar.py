@@ -208,24 +208,27 @@ def test_dynamic_rollout_many_handoffs_stress(kind, monkeypatch):
 
 
 @pytest.mark.parametrize("kind,n,T,workers,chunk", [
-    ("lorenz_rk4", 65536, 37, None, None),    # bench shape, default workers / chunk, short last chunk
-    ("lorenz_rk4", 65536, 64, "16", "1"),     # more workers than an SM has env-warps: the surplus waits
-    ("lorenz_rk4", 40000, 29, "12", "3"),     # ragged: partial last warp, SMs own 8 or 9 env-warps
-    ("lorenz_rk4", 70001, 33, "8", "8"),
+    ("lorenz_rk4", 65536, 37, None, None),    # bench shape: 12 residents + 1-2 guests per SM, short last chunk
+    ("lorenz_rk4", 65536, 64, "16", "1"),     # clamped to 13 residents: 0-1 guests, single-interval chunks
+    ("lorenz_rk4", 40000, 29, "12", "3"),     # ragged: partial last warp; SMs own 8 or 9 env-warps (8 residents)
+    ("lorenz_rk4", 70001, 33, "8", "8"),      # 8 residents + 6-7 guests: guests nearly alternate with own chunks
+    ("lorenz_rk4", 70001, 40, "3", "5"),      # 3 residents + 11-12 guests
     ("lorenz_rk4_f32", 65536, 26, None, "2"),
     ("pmsm_rk4", 50000, 21, None, None),
-    ("lorenz_rk4", 3000, 40, None, None),     # fewer env-warps (94) than SMs: one env-warp per block
+    ("lorenz_rk4", 3000, 40, None, None),     # fewer env-warps (94) than SMs: one env-warp per block, no guests
 ])
 def test_sm_local_rollout_is_bit_identical_to_static(kind, n, T, workers, chunk, monkeypatch):
-    """k_rollout_sm (per-SM task queue, env state / episode counters / staged actions in shared memory
-    for the whole launch) must reproduce the static one-thread-per-env kernel bit for bit, with
-    episodes ending (TimeLimit 11) inside the window, and so must the global-queue kernel it replaces."""
+    """k_rollout_sm (per SM: resident env-warps in registers for the whole launch, guest env-warps chunked
+    through a shared-memory queue, actions by tensor copies) must reproduce the static one-thread-per-env
+    kernel bit for bit, with episodes ending (TimeLimit 11) inside the window, with and without the tensor
+    map, and so must the global-queue kernel it replaces."""
     import torch
     kw = dict(seed=13, autoreset=True, max_episode_steps=11)
     res = {}
-    for mode in ("static", "sm", "dyn"):
+    for mode in ("static", "sm", "sm_rows", "dyn"):
         monkeypatch.setenv("CHAOS_B200_DYN", "0" if mode == "static" else "1")
         monkeypatch.setenv("CHAOS_B200_SM", "0" if mode == "dyn" else "1")
+        monkeypatch.setenv("CHAOS_B200_SM_TMAP", "0" if mode == "sm_rows" else "1")
         for k, v in (("CHAOS_B200_SM_WORKERS", workers), ("CHAOS_B200_SM_CHUNK", chunk)):
             if v is None:
                 monkeypatch.delenv(k, raising=False)
@@ -237,12 +240,12 @@ def test_sm_local_rollout_is_bit_identical_to_static(kind, n, T, workers, chunk,
         soa = ((torch.rand((T, b.act_dim, b.n_pad), generator=g) * 2 - 1) * float(b.layout.act_high)).to(b.device)
         out = b.rollout(T, soa[:, :, :n].permute(0, 2, 1))
         torch.cuda.synchronize()
-        assert b.sm_launch_count == (1 if mode == "sm" else 0), mode
+        assert b.sm_launch_count == (1 if mode.startswith("sm") else 0), mode
         assert b.dyn_launch_count == (0 if mode == "static" else 1), mode
         res[mode] = (out["obs"].clone(), out["reward"].clone(), out["done"].clone(), b.state.clone(),
                      b.ep_len.clone(), b.ep_return.clone(), b.stats())
         b.close()
-    for other in ("sm", "dyn"):
+    for other in ("sm", "sm_rows", "dyn"):
         for x, y in zip(res["static"][:6], res[other][:6]):
             assert torch.equal(torch.nan_to_num(x[..., :n].double()), torch.nan_to_num(y[..., :n].double())), other
         s0, s1 = res["static"][6], res[other][6]
