@@ -73,7 +73,8 @@ struct HostStage {
   cudaEvent_t ev_fork, ev_join;
   // CL_HOST_STREAMED: the step kernel is launched first and waits, block by block, for the slice of
   // the pinned action buffer it reads to be published (generation number) by the staging loop
-  uint32_t* h_ready;   // pinned [64] generation flags, one per slice
+  uint32_t* h_ready;   // pinned word: (generation << 8) | slices staged so far
+  uint32_t* d_ready;   // its device mirror, kept up to date by k_relay
   uint32_t* h_err;     // pinned: set by a block whose bounded wait expired
   uint32_t gen;
   uint8_t* d_warp_done;  // device copy for CL_HOST_DMA (travels with the result block)
@@ -224,6 +225,7 @@ static void host_stage_free(cl_ctx* ctx) {
   cudaFree(h.d_act); cudaFree(h.d_out);
   cudaFree(h.d_term); cudaFree(h.d_ler); cudaFree(h.d_lel);
   cudaFreeHost(h.h_ready);
+  cudaFree(h.d_ready);
   for (int k = 0; k < kHostRing; ++k) {
     cudaFreeHost(h.slot[k].out);
     cudaFreeHost(h.slot[k].term_obs); cudaFreeHost(h.slot[k].last_ep_ret); cudaFreeHost(h.slot[k].last_ep_len);
@@ -286,6 +288,26 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
 }
 
 __global__ void k_advance_step(uint64_t* step, uint64_t count) { *step += count; }
+
+__global__ void k_relay(const uint32_t* host_word, uint32_t* dev_word, uint32_t gen, uint32_t nslices, uint32_t* host_err) {
+  if (threadIdx.x != 0) return;
+  uint32_t last = 0, polls = 0;
+  uint64_t t0 = 0, t1 = 0;
+  for (;;) {
+    const uint32_t v = cl::ld_acquire_sys_u32(host_word);     // one system-scope read per ~4 us: the only one on the GPU
+    if ((v >> 8) == gen && (v & 255u) > last) {
+      last = v & 255u;
+      *(volatile uint32_t*)dev_word = v;
+      __threadfence();
+      if (last >= nslices) return;
+    }
+    if ((++polls & 63u) == 0u) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
+      if (t1 - t0 > 2000000000ull) { *host_err = 1u; return; }
+    }
+  }
+}
 
 static int launch(cl_ctx* ctx, const KParams& p_in, int mode, cudaStream_t st) {
   KParams p = p_in;
@@ -397,6 +419,7 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
   int chunk = CL_DYN_CHUNK_DEFAULT;
   if (const char* ov = getenv("CHAOS_B200_DYN_CHUNK")) { const int c = atoi(ov); if (c >= 1 && c <= 16) chunk = c; }
   int mode = cl::MODE_ROLLOUT;
+  alignas(64) CUtensorMap tmap;      // lives until launch() below has copied it into the kernel's parameters
   if (want_dynamic(ctx, d->T, chunk)) {
     const int64_t W = (ctx->cfg.num_envs + 31) / 32;
     if (!ctx->dyn_bps) {
@@ -444,7 +467,8 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
           if (sc > d->T) sc = d->T;
           if (cmax <= 64) {
             p.sm_grid = grid; p.sm_workers = workers; p.sm_chunk = sc;
-            p.sm_tmap_ok = action_tensor_map(&p.sm_tmap, io->action, (uint64_t)W * 32, (uint64_t)ctx->lay.act_dim,
+            p.host_tmap = &tmap;
+            p.sm_tmap_ok = action_tensor_map(&tmap, io->action, (uint64_t)W * 32, (uint64_t)ctx->lay.act_dim,
                                              (uint64_t)d->T, (uint64_t)io->act_cs, (uint64_t)d->act_ts, (uint32_t)sc) ? 1 : 0;
             const char* tm = getenv("CHAOS_B200_SM_TMAP");
             if (tm && tm[0] == '0') p.sm_tmap_ok = 0;
@@ -550,6 +574,8 @@ static int host_stage_init(cl_ctx* ctx) {
   memset(h.h_ready, 0, 80 * sizeof(uint32_t));
   h.h_err = h.h_ready + 72;
   h.gen = 0;
+  CU(cudaMalloc((void**)&h.d_ready, sizeof(uint32_t)));
+  CU(cudaMemset(h.d_ready, 0, sizeof(uint32_t)));
   h.d_obs = (float*)h.d_out;
   h.d_rew = (float*)(h.d_out + N * O * sizeof(float));
   h.d_done = (uint8_t*)(h.d_out + N * O * sizeof(float) + N * sizeof(float));
@@ -643,26 +669,37 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
   if (host_out) { memset(s.warp_done, 0, h.wd_bytes); p.warp_done = s.warp_done; p.host_rows = 1; }
   else { CU(cudaMemsetAsync(h.d_warp_done, 0, h.wd_bytes, st)); p.warp_done = h.d_warp_done; }
   if (mode == CL_HOST_STREAMED) {
-    // 1. launch: every block waits for the generation flag of the action slice it reads;
-    // 2. stage the caller's array slice by slice into the pinned buffer, publishing each slice.
-    // Nothing between the launch and the last flag store can fail, so the kernel always gets its flags
-    // (and its wait is bounded anyway).
+    // 1. launch k_relay (side stream: mirrors the pinned "slices staged" word into device memory) and
+    //    the step kernel, whose blocks wait for the slice they read;
+    // 2. stage the caller's array slice by slice into the pinned buffer, publishing the count after
+    //    each slice.  The final count is stored whatever happens in between, so both kernels always
+    //    terminate (and their waits are bounded anyway).
     const int blk = ctx->block;
     int slices = h.slices < 1 ? 1 : (h.slices > 64 ? 64 : h.slices);
     size_t per = ((N + (size_t)slices - 1) / (size_t)slices + (size_t)blk - 1) / (size_t)blk * (size_t)blk;   // whole blocks
-    h.gen += 1;
+    h.gen = (h.gen + 1) & 0x00FFFFFFu;
     if (h.gen == 0) h.gen = 1;
     *h.h_err = 0u;
-    p.act_ready = h.h_ready; p.act_gen = h.gen; p.act_slice_envs = (int32_t)per; p.host_err = h.h_err;
-    { const char* ov = getenv("CHAOS_B200_POLL"); p.act_poll = (ov && ov[0] == '1') ? 1 : 0; }
-    r = launch(ctx, p, cl::MODE_STEP, st);
-    if (r) return r;
-    int j = 0;
-    for (size_t b = 0; b < N; b += per, ++j) {
-      const size_t e = b + per < N ? b + per : N;
-      memcpy(h.h_act + b * A, action_host + b * A, (e - b) * A * sizeof(float));
-      __atomic_store_n(&h.h_ready[j], h.gen, __ATOMIC_RELEASE);
+    const uint32_t nsl = (uint32_t)((N + per - 1) / per);
+    __atomic_store_n(&h.h_ready[0], h.gen << 8, __ATOMIC_RELEASE);
+    p.act_ready = h.d_ready; p.act_gen = h.gen; p.act_slice_envs = (int32_t)per; p.host_err = h.h_err;
+    k_relay<<<1, 32, 0, h.side>>>(h.h_ready, h.d_ready, h.gen, nsl, h.h_err);
+    if (cudaGetLastError() != cudaSuccess) {
+      __atomic_store_n(&h.h_ready[0], (h.gen << 8) | nsl, __ATOMIC_RELEASE);
+      return fail(ctx, CL_ECUDA, "relay kernel launch failed");
     }
+    r = launch(ctx, p, cl::MODE_STEP, st);
+    uint32_t j = 0;
+    if (r == CL_OK) {
+      for (size_t b = 0; b < N; b += per) {
+        const size_t e = b + per < N ? b + per : N;
+        memcpy(h.h_act + b * A, action_host + b * A, (e - b) * A * sizeof(float));
+        __atomic_store_n(&h.h_ready[0], (h.gen << 8) | ++j, __ATOMIC_RELEASE);
+      }
+    }
+    // whatever happened, the relay (and any block already running) must see the final count
+    __atomic_store_n(&h.h_ready[0], (h.gen << 8) | nsl, __ATOMIC_RELEASE);
+    if (r) return r;
   } else if (mode == CL_HOST_PIPELINED && h.slices > 1) {
     // slice j runs on stream (j & 1): [DMA its actions in] -> [kernel: step, write results to host].
     // The user's array is staged into pinned memory slice by slice too, so that host memcpy

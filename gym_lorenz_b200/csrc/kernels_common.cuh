@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/chaos_b200.h"
 #include "philox.cuh"
@@ -50,7 +51,7 @@ struct KParams {
   int32_t host_rows;
   const uint32_t* act_ready;
   uint32_t act_gen;
-  int32_t act_poll;        // 0: relaxed volatile polling (default), 1: ld.acquire.sys (A/B only)
+  int32_t act_poll;        // unused (kept for ABI stability of the struct within this round)
   int32_t act_slice_envs;
   uint32_t* host_err;
   // rollout
@@ -78,8 +79,8 @@ struct KParams {
   int32_t dyn_chunk, dyn_nchunks, dyn_nwarps, dyn_tma, dyn_grid;
   // SM-local rollout scheduling (k_rollout_sm): grid, worker warps per block, control intervals per task
   int32_t sm_grid, sm_workers, sm_chunk;
-  int32_t sm_tmap_ok;                  // sm_tmap describes the action tensor (x env, y channel, z interval)
-  alignas(64) CUtensorMap sm_tmap;
+  int32_t sm_tmap_ok;                  // *host_tmap describes the action tensor (x env, y channel, z interval)
+  const CUtensorMap* host_tmap;        // host-side only: passed to k_rollout_sm as its own __grid_constant__ parameter
   // observations go out as contiguous, 16-byte aligned float32 rows -> warp-transposed vector stores
   int32_t rows_fast;
   int32_t no_plain;  // host-side only: keep the generic instantiation (tests, A/B runs)
@@ -146,6 +147,9 @@ __device__ __forceinline__ uint64_t step_base(const KParams& p) {
 // counter (a per-block completion ticket would put one same-address atomic per block on the
 // critical path: +35 us at 16,384 blocks).
 __global__ void k_advance_step(uint64_t* step, uint64_t count);
+// Streamed host mode: mirrors the pinned "slices staged" word (gen << 8 | count) into device memory until
+// all `nslices` of generation `gen` are published (bounded: ~2 s).
+__global__ void k_relay(const uint32_t* host_word, uint32_t* dev_word, uint32_t gen, uint32_t nslices, uint32_t* host_err);
 
 // n uniforms in [lo,hi) (NumPy construction), 2 per Philox block.
 template <int N>
@@ -506,25 +510,28 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
   const bool streamed = !ROLL && p.act_ready != nullptr;   // block-uniform
   if (streamed) {
     // Streamed host mode: this kernel was launched BEFORE the CPU finished staging the caller's action
-    // array into the pinned buffer.  The CPU publishes slice j (act_slice_envs envs, a whole number of
-    // blocks) by storing the step's generation number into act_ready[j]; the block's first thread polls
-    // that word over PCIe, the state loads above are already in flight meanwhile.  Bounded wait: after
-    // ~2 s the block gives up, flags the error for cl_step_host_wait and proceeds.
+    // array into the pinned buffer.  The CPU publishes the number of slices staged so far (act_slice_envs
+    // envs each, a whole number of blocks) in a pinned word; k_relay (one thread, side stream) mirrors
+    // that word into device memory, and every block polls the DEVICE copy: uncached reads of host memory
+    // cost ~4 us each and are served one at a time (measured: 1 ms per step when all 256 blocks polled
+    // the host word themselves), a device word is an L2 hit.  The state loads above are already in
+    // flight meanwhile.  Bounded wait: after ~2 s the block flags the error for cl_step_host_wait.
     if (threadIdx.x == 0) {
-      // Relaxed (volatile) polling, no system-scope fence per poll.  Ordering of the action loads behind
-      // the flag: they are issued after the branch on the flag value resolved (no speculation past it) and
-      // after the block barrier below; the CPU publishes with a release store after writing the slice.
-      const volatile uint32_t* flag = p.act_ready + (i - p.i_begin) / p.act_slice_envs;
+      const uint32_t need = (uint32_t)((i - p.i_begin) / p.act_slice_envs) + 1u;
+      const volatile uint32_t* word = p.act_ready;
       uint64_t t0 = 0, t1 = 0;
       uint32_t polls = 0;
-      while ((p.act_poll == 1 ? ld_acquire_sys_u32((const uint32_t*)flag) : *flag) != p.act_gen) {
-        __nanosleep(100);
+      for (;;) {
+        const uint32_t v = *word;
+        if ((v >> 8) == p.act_gen && (v & 255u) >= need) break;
+        __nanosleep(200);
         if ((++polls & 63u) == 0u) {
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
           if (t0 == 0) t0 = t1;
           if (t1 - t0 > 2000000000ull) { if (p.host_err) *p.host_err = 1u; break; }
         }
       }
+      __threadfence();   // the relay's device store is ordered after its (system-scope) read of the host word
     }
     __syncthreads();
   }
@@ -842,7 +849,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int x, 
 // instead of 3 issue cycles, tools/dfma_probe.cu); (512, 0) gives 1 of 128, (384, 0) 76 of 128 --
 // checked on the built library by tests/test_sass.py with tools/sass_mix.py
 template <class E>
-__global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const __grid_constant__ KParams p) {
+// The tensor map is its own __grid_constant__ parameter (the descriptor must be addressable in param
+// space); KParams stays an ordinary by-value parameter -- as a __grid_constant__ it faulted on sm_100a.
+__global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const KParams p,
+                                                                         const __grid_constant__ CUtensorMap tmap) {
   typedef typename E::real real;
   extern __shared__ __align__(128) unsigned char sm_raw[];
   const unsigned lane = threadIdx.x & 31u;
@@ -895,7 +905,7 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
       // barrier's transaction bytes, rows past T arrive as zeros
       if (lane == 0) {
         mbar_expect_tx(bar, (uint32_t)(per_buf * sizeof(float)));
-        tma_load_3d(dst, &p.sm_tmap, (e0 + le) * 32, 0, t0, bar);
+        tma_load_3d(dst, &tmap, (e0 + le) * 32, 0, t0, bar);
       }
     } else {
       const int len = chunk_len(f, c);
@@ -1139,7 +1149,11 @@ cudaError_t launch_env(const KParams& p_in, int mode, cudaStream_t st, int block
               attr_set = true;
             }
             if (p_in.host_plain_out) *p_in.host_plain_out |= 2;
-            k_rollout_sm<E><<<(unsigned)p.sm_grid, (unsigned)p.sm_workers * 32, smem, st>>>(p);
+            alignas(64) CUtensorMap tm;
+            if (p.sm_tmap_ok && p.host_tmap) tm = *p.host_tmap;
+            else { memset(&tm, 0, sizeof(tm)); p.sm_tmap_ok = 0; }
+            p.host_tmap = nullptr;
+            k_rollout_sm<E><<<(unsigned)p.sm_grid, (unsigned)p.sm_workers * 32, smem, st>>>(p, tm);
             break;
           }
         }

@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 KERNELS = {
-    "f64": "_ZN2cl12k_rollout_smINS_12EnvLorenzRK4IdEEEEvNS_7KParamsE",
-    "f32": "_ZN2cl12k_rollout_smINS_12EnvLorenzRK4IfEEEEvNS_7KParamsE",
+    "f64": "_ZN2cl12k_rollout_smINS_12EnvLorenzRK4IdEEEEvNS_7KParamsE14CUtensorMap_st",
+    "f32": "_ZN2cl12k_rollout_smINS_12EnvLorenzRK4IfEEEEvNS_7KParamsE14CUtensorMap_st",
 }
 
 
