@@ -62,7 +62,7 @@ def full_metrics():
         return int(v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u])
     tj = {"workload": {"kind": "lorenz_rk4", "envs": 65536, "chunk": 256, "substeps": 16}, "kernel": name,
           "dram_bytes_read": to_bytes("dram__bytes_read.sum"), "dram_bytes_write": to_bytes("dram__bytes_write.sum"),
-          "source": f"ncu --set full --clock-control none -k regex:k_rollout_dyn ({tag} build); summary: "
+          "source": f"ncu --set full --clock-control none -k regex:k_rollout_sm ({tag} build, tools/r02_prof.sh); summary: "
                     f"profiles/{tag}_dyn_ncu_full_metrics.txt"}
     json.dump(tj, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     # per-instruction sampling: top stall sites
