@@ -462,7 +462,10 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
           workers = workers > 16 ? 16 : workers;
           if (workers == 16 && qn < 20) workers = 12;   // 16..19 env-warps: 12 residents + 4..7 guests balance better than 16 + 0..3
           if (const char* w = getenv("CHAOS_B200_SM_WORKERS")) { const int k = atoi(w); if (k >= 1 && k <= 16) workers = k < qn ? k : qn; }
-          int sc = 8;
+          // control intervals per chunk: 16 if the action double buffers of the block's env-warps fit
+          // (each env-warp: 2 x chunk x ACT x 128 B), else 8, 4, ... (+0.8 % from 8 to 16, -2 % from 8 to 4)
+          int sc = 16;
+          while (sc > 1 && (size_t)cmax * (2u * (size_t)sc * (size_t)ctx->lay.act_dim * 128u + 2048u) > 190u * 1024u) sc /= 2;
           if (const char* w = getenv("CHAOS_B200_SM_CHUNK")) { const int k = atoi(w); if (k >= 1 && k <= 16) sc = k; }
           if (sc > d->T) sc = d->T;
           if (cmax <= 64) {
@@ -547,13 +550,15 @@ extern "C" int cl_block_size(const cl_ctx* ctx) { return ctx ? ctx->block : 0; }
 // ---- host-buffer path ------------------------------------------------------------------
 
 // Default data-movement mode of the host path per (env kind, batch size), from the measured table in
-// profiles/r02_e2e_host_modes.jsonl (tools/e2e_modes.py: every kind x {4,096, 16,384, 65,536} envs x every
-// mode, fresh caller-owned action array each step).
+// profiles/r02_e2e_host_modes.jsonl (tools/e2e_modes.py: lorenz_rk4 / hr_sync / pmsm_sync x {4,096, 65,536}
+// envs x every mode, fresh caller-owned action array each step).  At 65,536 envs: lorenz_rk4 113 (zero-copy)
+// -> 88 us (streamed, 16 slices), pmsm_sync 91 -> 76, hr_sync 138 -> 123 (DMA chain: 137 / 113 / 147); at
+// 4,096 envs all within 2 us of each other.  The kind does not change the ranking, so it does not enter.
 static void host_mode_default(int kind, int64_t n, int* mode, int* slices) {
   (void)kind;
-  *mode = CL_HOST_STREAMED;
-  int k = (int)(n / 8192);
-  *slices = k < 1 ? 1 : (k > 16 ? 16 : k);
+  *mode = CL_HOST_STREAMED;            // never slower than ZEROCOPY in the table, 10-25 % faster from 16,384 envs up
+  int k = (int)(n / 2048);             // finer slices keep paying up to the relay's poll period (~4 us of staging)
+  *slices = k < 1 ? 1 : (k > 64 ? 64 : k);
 }
 
 static int host_stage_init(cl_ctx* ctx) {
