@@ -465,7 +465,8 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
           // control intervals per chunk: 16 if the action double buffers of the block's env-warps fit
           // (each env-warp: 2 x chunk x ACT x 128 B), else 8, 4, ... (+0.8 % from 8 to 16, -2 % from 8 to 4)
           int sc = 16;
-          while (sc > 1 && (size_t)cmax * (2u * (size_t)sc * (size_t)ctx->lay.act_dim * 128u + 2048u) > 190u * 1024u) sc /= 2;
+          const size_t per_warp = (size_t)ctx->lay.n_state * 32u * (size_t)ctx->lay.real_bytes + 32u * 12u + 28u;   // SmLayout
+          while (sc > 1 && (size_t)cmax * (2u * (size_t)sc * (size_t)ctx->lay.act_dim * 128u + per_warp) + 256u > 200u * 1024u) sc /= 2;
           if (const char* w = getenv("CHAOS_B200_SM_CHUNK")) { const int k = atoi(w); if (k >= 1 && k <= 16) sc = k; }
           if (sc > d->T) sc = d->T;
           if (cmax <= 64) {
@@ -559,6 +560,42 @@ static void host_mode_default(int kind, int64_t n, int* mode, int* slices) {
   *mode = CL_HOST_STREAMED;            // never slower than ZEROCOPY in the table, 10-25 % faster from 16,384 envs up
   int k = (int)(n / 2048);             // finer slices keep paying up to the relay's poll period (~4 us of staging)
   *slices = k < 1 ? 1 : (k > 64 ? 64 : k);
+}
+
+// Staging copy caller array -> pinned buffer with non-temporal (streaming) stores: the destination is
+// written once and next read by the GPU over PCIe, so allocating its lines in the CPU caches first
+// (a read-for-ownership per line with ordinary stores) only costs memory bandwidth.  AVX2 when the CPU has
+// it, memcpy otherwise and for the unaligned edges.  Ends with a store fence: the "slice staged" word that
+// follows must not overtake the weakly ordered streaming stores.
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void stream_copy_avx2(unsigned char* d, const unsigned char* s, size_t n) {
+  size_t head = (32 - ((uintptr_t)d & 31)) & 31;
+  if (head > n) head = n;
+  if (head) { memcpy(d, s, head); d += head; s += head; n -= head; }
+  size_t k = 0;
+  for (; k + 128 <= n; k += 128) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)(s + k)), b = _mm256_loadu_si256((const __m256i*)(s + k + 32));
+    const __m256i c = _mm256_loadu_si256((const __m256i*)(s + k + 64)), e = _mm256_loadu_si256((const __m256i*)(s + k + 96));
+    _mm256_stream_si256((__m256i*)(d + k), a); _mm256_stream_si256((__m256i*)(d + k + 32), b);
+    _mm256_stream_si256((__m256i*)(d + k + 64), c); _mm256_stream_si256((__m256i*)(d + k + 96), e);
+  }
+  for (; k + 32 <= n; k += 32) _mm256_stream_si256((__m256i*)(d + k), _mm256_loadu_si256((const __m256i*)(s + k)));
+  if (k < n) memcpy(d + k, s + k, n - k);
+  _mm_sfence();
+}
+#endif
+static void stage_copy_bytes(void* dst, const void* src, size_t n) {
+#if defined(__x86_64__)
+  static int mode = -1;   // 1: AVX2 streaming stores, 0: memcpy
+  if (mode < 0) {
+    const char* ov = getenv("CHAOS_B200_STAGE_COPY");   // "memcpy" | "stream" (tuning / A-B)
+    mode = __builtin_cpu_supports("avx2") ? 1 : 0;
+    if (ov && !strcmp(ov, "memcpy")) mode = 0;
+  }
+  if (mode == 1 && n >= 4096) { stream_copy_avx2((unsigned char*)dst, (const unsigned char*)src, n); return; }
+#endif
+  memcpy(dst, src, n);
 }
 
 static int host_stage_init(cl_ctx* ctx) {
@@ -698,7 +735,7 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
     if (r == CL_OK) {
       for (size_t b = 0; b < N; b += per) {
         const size_t e = b + per < N ? b + per : N;
-        memcpy(h.h_act + b * A, action_host + b * A, (e - b) * A * sizeof(float));
+        stage_copy_bytes(h.h_act + b * A, action_host + b * A, (e - b) * A * sizeof(float));
         __atomic_store_n(&h.h_ready[0], (h.gen << 8) | ++j, __ATOMIC_RELEASE);
       }
     }
@@ -726,7 +763,7 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
     CU(cudaEventRecord(h.ev_join, h.side));
     CU(cudaStreamWaitEvent(st, h.ev_join, 0));
   } else {
-    if (stage_copy) memcpy(h.h_act, action_host, N * A * sizeof(float));
+    if (stage_copy) stage_copy_bytes(h.h_act, action_host, N * A * sizeof(float));
     if (!host_in) CU(cudaMemcpyAsync(h.d_act, h.h_act, N * A * sizeof(float), cudaMemcpyHostToDevice, st));
     r = launch(ctx, p, cl::MODE_STEP, st);
     if (r) return r;

@@ -18,7 +18,7 @@ for kind in kinds:
     b = ChaosBatch(kind, n, seed=0)
     b.reset()
     a = (torch.rand((n, b.act_dim), device=dev) * 2 - 1) * AMP.get(kind, 1.0)
-    for _ in range(4):
+    for _ in range(2):
         b.step(a)
     torch.cuda.synchronize()
     b.close()
@@ -32,7 +32,7 @@ if "rl_ops" in kinds or len(sys.argv) <= 1:
     term = torch.zeros_like(stacked)
     done = (torch.rand(N, device=dev) < 0.01).to(torch.uint8)
     lib = rl_ops.L.load()
-    for _ in range(3):
+    for _ in range(2):
         rms.update(obs)
         lib.cl_obs_normalize(rl_ops._stream(dev), rl_ops._p(obs), obs.stride(0), obs.stride(1), rl_ops._p(out), D, 1, N, D,
                              rl_ops._p(rms.mean), rl_ops._p(rms.var), 1e-8, 10.0)
@@ -40,10 +40,10 @@ if "rl_ops" in kinds or len(sys.argv) <= 1:
                                 D, 1, rl_ops._p(term), N, D, K)
     T, NE = 128, 65536
     r, v, s = (torch.randn((T, NE), device=dev) for _ in range(3))
-    for _ in range(3):
+    for _ in range(2):
         rl_ops.gae(r, v, (s > 1).float(), v[0], (s[0] > 1).float(), 0.99, 0.95)
     e, u = torch.randn((2000, 3, 16384), device=dev, dtype=torch.float64), torch.randn((2000, 2, 16384), device=dev, dtype=torch.float64)
-    for _ in range(3):
+    for _ in range(2):
         rl_ops.eval_metrics(e, u, dt=0.001)
     torch.cuda.synchronize()
 print("done")

@@ -7,23 +7,26 @@
 TAG=${1:-r02}
 O=gpurun_out
 T="timeout -k 5"
-$T 900 python -m pytest tests -q -m gpu --durations=8 > $O/pytest_gpu_$TAG.log 2>&1; echo "full suite rc=$?"; tail -14 $O/pytest_gpu_$TAG.log
+if [ "$SKIP_TESTS" != 1 ]; then $T 900 python -m pytest tests -q -m gpu --durations=8 > $O/pytest_gpu_$TAG.log 2>&1; echo "full suite rc=$?"; tail -4 $O/pytest_gpu_$TAG.log; fi
 $T 600 python bench.py > $O/bench_$TAG.json 2> $O/bench_$TAG.err || tail -5 $O/bench_$TAG.err
 $T 300 python bench.py --impl reference --steps 20 --warmup 3 > $O/bench_reference_$TAG.json 2>> $O/bench_$TAG.err
 $T 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$TAG.csv \
     python bench.py --steps 20 --warmup 3 --e2e-chunks 1 --no-cpu-baseline > $O/ncu_launch_$TAG.log 2>&1
-$T 600 ncu --set full --clock-control none --import-source on -k regex:k_rollout_sm -s 4 -c 2 -f -o $O/prof_dyn_$TAG \
+$T 600 ncu --set full --clock-control none --import-source on -k regex:k_rollout_sm -s 4 -c 1 -f -o $O/prof_dyn_$TAG \
     python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_full_$TAG.log 2>&1
 $T 600 ncu --set full --clock-control none --import-source on -k regex:k_rollout_sm -s 4 -c 1 -f -o $O/prof_dyn_f32_$TAG \
     python bench.py --kind lorenz_rk4_f32 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_full_f32_$TAG.log 2>&1
 $T 600 ncu --set full --clock-control none --import-source on -k regex:k_rollout_sm -s 4 -c 1 -f -o $O/prof_dyn_pmsm_$TAG \
     python bench.py --kind pmsm_rk4 --substeps 4 --param-jitter 0.1 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_full_pmsm_$TAG.log 2>&1
-$T 900 ncu --set full --clock-control none --import-source on -k regex:'k_step|k_gae|k_moments|k_normalize|k_frame_stack|k_eval|k_rms' -f -o $O/prof_hbm_$TAG \
+# the gpurun_out merge is capped at 64 MiB per call: no source import for the many small kernels
+$T 900 ncu --set full --clock-control none -k regex:'k_step|k_gae|k_moments|k_normalize|k_frame_stack|k_eval|k_rms' -f -o $O/prof_hbm_$TAG \
     python tools/profile_hbm_kernels.py > $O/ncu_hbm_$TAG.log 2>&1
 ls -la $O/*.ncu-rep
 $T 600 python tools/sweep.py --sizes 1048576 > $O/sweep_$TAG.jsonl 2> $O/sweep_$TAG.err
 $T 120 python tools/trace_tensor_path.py > $O/trace_tensor_path_$TAG.json 2> $O/trace_$TAG.err
-$T 200 python tools/e2e_modes.py lorenz_rk4 16384,65536 zerocopy:1,streamed:8,streamed:16,streamed:32,streamed:64 > $O/e2e_slices_$TAG.jsonl 2>> $O/trace_$TAG.err
+$T 200 python tools/e2e_modes.py lorenz_rk4 65536 zerocopy:1,streamed:16,streamed:32 > $O/e2e_slices_$TAG.jsonl 2>> $O/trace_$TAG.err
+CHAOS_B200_STAGE_COPY=memcpy $T 200 python tools/e2e_modes.py lorenz_rk4 65536 zerocopy:1,streamed:16,streamed:32 > $O/e2e_slices_memcpy_$TAG.jsonl 2>> $O/trace_$TAG.err
+cat $O/e2e_slices_memcpy_$TAG.jsonl
 for cfg in "--kind pmsm_rk4 --substeps 4 --param-jitter 0.1" "--param-jitter 0.1" "--kind lorenz_rk4_f32" "--envs-per-gpu 1048576 --chunk 16" "--envs-per-gpu 1048576 --chunk 16 --kind lorenz_rk4_f32" "--envs-per-gpu 1048576 --chunk 16 --kind pmsm_rk4 --substeps 4 --param-jitter 0.1"; do
   $T 300 python bench.py --steps 300 --warmup 5 --no-e2e --no-cpu-baseline $cfg 2>/dev/null | tail -1 >> $O/cfg_1gpu_$TAG.jsonl
 done
