@@ -1,17 +1,23 @@
 // C-ABI implementation (include/chaos_b200.h): context, argument validation, kernel
 // dispatch, pinned host staging for the SB3 numpy contract, measurement utilities.
 #include <math.h>
+#include <pthread.h>
+#include <sched.h>
 #include <stdarg.h>
+#include <time.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "kernels_common.cuh"
+#include "host_copy.h"
 
 cudaError_t cl_launch_derivatives(int kind, const void* state, const float* action, void* out,
                                   int64_t n, cudaStream_t st);
 
 using cl::KParams;
+
+struct CopyHelper;
 
 namespace {
 
@@ -79,6 +85,7 @@ struct HostStage {
   uint32_t gen;
   uint8_t* d_warp_done;  // device copy for CL_HOST_DMA (travels with the result block)
   size_t wd_bytes;
+  struct CopyHelper* helper;   // second staging thread (nullptr: single-threaded staging)
 };
 
 }  // namespace
@@ -218,9 +225,13 @@ extern "C" int cl_create(const cl_config* cfg, cl_ctx** out) {
   return CL_OK;
 }
 
+static void copy_helper_stop(CopyHelper* c);
+
 static void host_stage_free(cl_ctx* ctx) {
   HostStage& h = ctx->hs;
   if (!h.ready) return;
+  copy_helper_stop(h.helper);
+  h.helper = nullptr;
   cudaFreeHost(h.h_act);
   cudaFree(h.d_act); cudaFree(h.d_out);
   cudaFree(h.d_term); cudaFree(h.d_ler); cudaFree(h.d_lel);
@@ -562,42 +573,6 @@ static void host_mode_default(int kind, int64_t n, int* mode, int* slices) {
   *slices = k < 1 ? 1 : (k > 64 ? 64 : k);
 }
 
-// Staging copy caller array -> pinned buffer with non-temporal (streaming) stores: the destination is
-// written once and next read by the GPU over PCIe, so allocating its lines in the CPU caches first
-// (a read-for-ownership per line with ordinary stores) only costs memory bandwidth.  AVX2 when the CPU has
-// it, memcpy otherwise and for the unaligned edges.  Ends with a store fence: the "slice staged" word that
-// follows must not overtake the weakly ordered streaming stores.
-#if defined(__x86_64__)
-#include <immintrin.h>
-__attribute__((target("avx2"))) static void stream_copy_avx2(unsigned char* d, const unsigned char* s, size_t n) {
-  size_t head = (32 - ((uintptr_t)d & 31)) & 31;
-  if (head > n) head = n;
-  if (head) { memcpy(d, s, head); d += head; s += head; n -= head; }
-  size_t k = 0;
-  for (; k + 128 <= n; k += 128) {
-    const __m256i a = _mm256_loadu_si256((const __m256i*)(s + k)), b = _mm256_loadu_si256((const __m256i*)(s + k + 32));
-    const __m256i c = _mm256_loadu_si256((const __m256i*)(s + k + 64)), e = _mm256_loadu_si256((const __m256i*)(s + k + 96));
-    _mm256_stream_si256((__m256i*)(d + k), a); _mm256_stream_si256((__m256i*)(d + k + 32), b);
-    _mm256_stream_si256((__m256i*)(d + k + 64), c); _mm256_stream_si256((__m256i*)(d + k + 96), e);
-  }
-  for (; k + 32 <= n; k += 32) _mm256_stream_si256((__m256i*)(d + k), _mm256_loadu_si256((const __m256i*)(s + k)));
-  if (k < n) memcpy(d + k, s + k, n - k);
-  _mm_sfence();
-}
-#endif
-static void stage_copy_bytes(void* dst, const void* src, size_t n) {
-#if defined(__x86_64__)
-  static int mode = -1;   // 1: AVX2 streaming stores, 0: memcpy
-  if (mode < 0) {
-    const char* ov = getenv("CHAOS_B200_STAGE_COPY");   // "memcpy" | "stream" (tuning / A-B)
-    mode = __builtin_cpu_supports("avx2") ? 1 : 0;
-    if (ov && !strcmp(ov, "memcpy")) mode = 0;
-  }
-  if (mode == 1 && n >= 4096) { stream_copy_avx2((unsigned char*)dst, (const unsigned char*)src, n); return; }
-#endif
-  memcpy(dst, src, n);
-}
-
 static int host_stage_init(cl_ctx* ctx) {
   HostStage& h = ctx->hs;
   if (h.ready) return CL_OK;
@@ -656,6 +631,7 @@ static int host_stage_init(cl_ctx* ctx) {
     else if (!strcmp(ov, "streamed")) h.mode = CL_HOST_STREAMED;
   }
   if (const char* ov = getenv("CHAOS_B200_HOST_SLICES")) { const int k = atoi(ov); if (k >= 1 && k <= 64) h.slices = k; }
+  h.helper = copy_helper_start(N * A * sizeof(float));
   h.ready = true;
   return CL_OK;
 }
@@ -731,14 +707,9 @@ extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* b
       return fail(ctx, CL_ECUDA, "relay kernel launch failed");
     }
     r = launch(ctx, p, cl::MODE_STEP, st);
-    uint32_t j = 0;
-    if (r == CL_OK) {
-      for (size_t b = 0; b < N; b += per) {
-        const size_t e = b + per < N ? b + per : N;
-        stage_copy_bytes(h.h_act + b * A, action_host + b * A, (e - b) * A * sizeof(float));
-        __atomic_store_n(&h.h_ready[0], (h.gen << 8) | ++j, __ATOMIC_RELEASE);
-      }
-    }
+    if (r == CL_OK)
+      stage_slices(h.helper, (unsigned char*)h.h_act, (const unsigned char*)action_host, per * A * sizeof(float),
+                   N * A * sizeof(float), nsl, h.gen, h.h_ready);
     // whatever happened, the relay (and any block already running) must see the final count
     __atomic_store_n(&h.h_ready[0], (h.gen << 8) | nsl, __ATOMIC_RELEASE);
     if (r) return r;

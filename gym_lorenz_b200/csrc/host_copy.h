@@ -1,0 +1,154 @@
+// Host-side staging of a caller-owned action array into the pinned buffer the step kernel reads
+// (cl_step_host_async, streamed mode): streaming-store copy, optional second copy thread, monotonic
+// publication of the "slices staged" word.  Plain C++ (no CUDA) so that the protocol can be stress-tested
+// on the CPU (tests/test_host_copy_cpu.py).
+#pragma once
+#include <pthread.h>
+#include <sched.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+// ---- second staging thread ------------------------------------------------------------------
+// A single core copies the caller's action array into pinned memory at 12-16 GB/s (50 us for the 786 KB
+// of 65,536 Lorenz envs): in streamed mode that copy, not PCIe, is what the step waits for.  A helper
+// thread takes every other slice.  It spins (pause) while steps keep coming, naps in 100 us sleeps once
+// the env has been idle for 2 ms, and is joined by cl_destroy.  Off when the process may use fewer than
+// 4 cores, for batches whose actions are under 64 KB, or with CHAOS_B200_COPY_THREADS=1.
+struct CopyHelper {
+  pthread_t th;
+  bool started;
+  volatile uint32_t job_gen;     // bumped by the stepping thread to start a job
+  volatile uint32_t quit;
+  // job (written before job_gen, read after): odd slices of [0, nsl)
+  unsigned char* dst;
+  const unsigned char* src;
+  size_t per_bytes, total_bytes;
+  uint32_t nsl, word_gen;
+  volatile uint32_t main_done, helper_done;   // slices finished by each thread
+  uint32_t* word;                // pinned "slices staged" word, advanced monotonically by both threads
+};
+
+static void stage_copy_bytes(void* dst, const void* src, size_t n);
+
+// contiguous prefix of staged slices: evens < 2m done by the stepping thread, odds < 2k + ... by the helper
+static void publish_prefix(CopyHelper* c) {
+  const uint32_t m = c->main_done, k = c->helper_done;
+  uint32_t p = (m <= k) ? 2 * m : 2 * k + 1;
+  if (p > c->nsl) p = c->nsl;
+  const uint32_t want = (c->word_gen << 8) | p;
+  uint32_t cur = __atomic_load_n(c->word, __ATOMIC_RELAXED);
+  while ((cur >> 8) == c->word_gen && (cur & 255u) < p &&
+         !__atomic_compare_exchange_n(c->word, &cur, want, false, __ATOMIC_RELEASE, __ATOMIC_RELAXED)) {}
+}
+
+static void* copy_helper_main(void* arg) {
+  CopyHelper* c = (CopyHelper*)arg;
+  uint32_t seen = 0;
+  uint64_t idle = 0;
+  while (!__atomic_load_n(&c->quit, __ATOMIC_ACQUIRE)) {
+    const uint32_t g = __atomic_load_n(&c->job_gen, __ATOMIC_ACQUIRE);
+    if (g == seen) {
+      if (++idle < 400000) { __builtin_ia32_pause(); }
+      else { struct timespec ts = {0, 100000}; nanosleep(&ts, nullptr); }
+      continue;
+    }
+    seen = g;
+    idle = 0;
+    for (uint32_t j = 1; j < c->nsl; j += 2) {
+      const size_t b = (size_t)j * c->per_bytes;
+      const size_t e = b + c->per_bytes < c->total_bytes ? b + c->per_bytes : c->total_bytes;
+      stage_copy_bytes(c->dst + b, c->src + b, e - b);
+      __atomic_store_n(&c->helper_done, c->helper_done + 1, __ATOMIC_RELEASE);
+      publish_prefix(c);
+    }
+  }
+  return nullptr;
+}
+
+static CopyHelper* copy_helper_start(size_t action_bytes) {
+  int threads = 2;
+  if (const char* ov = getenv("CHAOS_B200_COPY_THREADS")) threads = atoi(ov);
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  const int cores = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
+  if (threads < 2 || cores < 4 || action_bytes < 64 * 1024) return nullptr;
+  CopyHelper* c = (CopyHelper*)calloc(1, sizeof(CopyHelper));
+  if (!c) return nullptr;
+  if (pthread_create(&c->th, nullptr, copy_helper_main, c) != 0) { free(c); return nullptr; }
+  c->started = true;
+  return c;
+}
+
+static void copy_helper_stop(CopyHelper* c) {
+  if (!c) return;
+  __atomic_store_n(&c->quit, 1u, __ATOMIC_RELEASE);
+  if (c->started) pthread_join(c->th, nullptr);
+  free(c);
+}
+
+// Staging copy caller array -> pinned buffer with non-temporal (streaming) stores: the destination is
+// written once and next read by the GPU over PCIe, so allocating its lines in the CPU caches first
+// (a read-for-ownership per line with ordinary stores) only costs memory bandwidth.  AVX2 when the CPU has
+// it, memcpy otherwise and for the unaligned edges.  Ends with a store fence: the "slice staged" word that
+// follows must not overtake the weakly ordered streaming stores.
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void stream_copy_avx2(unsigned char* d, const unsigned char* s, size_t n) {
+  size_t head = (32 - ((uintptr_t)d & 31)) & 31;
+  if (head > n) head = n;
+  if (head) { memcpy(d, s, head); d += head; s += head; n -= head; }
+  size_t k = 0;
+  for (; k + 128 <= n; k += 128) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)(s + k)), b = _mm256_loadu_si256((const __m256i*)(s + k + 32));
+    const __m256i c = _mm256_loadu_si256((const __m256i*)(s + k + 64)), e = _mm256_loadu_si256((const __m256i*)(s + k + 96));
+    _mm256_stream_si256((__m256i*)(d + k), a); _mm256_stream_si256((__m256i*)(d + k + 32), b);
+    _mm256_stream_si256((__m256i*)(d + k + 64), c); _mm256_stream_si256((__m256i*)(d + k + 96), e);
+  }
+  for (; k + 32 <= n; k += 32) _mm256_stream_si256((__m256i*)(d + k), _mm256_loadu_si256((const __m256i*)(s + k)));
+  if (k < n) memcpy(d + k, s + k, n - k);
+  _mm_sfence();
+}
+#endif
+static void stage_copy_bytes(void* dst, const void* src, size_t n) {
+#if defined(__x86_64__)
+  static int mode = -1;   // 1: AVX2 streaming stores, 0: memcpy
+  if (mode < 0) {
+    const char* ov = getenv("CHAOS_B200_STAGE_COPY");   // "memcpy" | "stream" (tuning / A-B)
+    mode = __builtin_cpu_supports("avx2") ? 1 : 0;
+    if (ov && !strcmp(ov, "memcpy")) mode = 0;
+  }
+  if (mode == 1 && n >= 4096) { stream_copy_avx2((unsigned char*)dst, (const unsigned char*)src, n); return; }
+#endif
+  memcpy(dst, src, n);
+}
+
+
+// Stage `total_bytes` from src to dst in `nsl` slices of `per_bytes`, publishing (gen << 8) | slices-staged
+// in *word after every slice.  With a helper: even slices here, odd slices on the helper thread.
+static void stage_slices(CopyHelper* c, unsigned char* dst, const unsigned char* src, size_t per_bytes,
+                         size_t total_bytes, uint32_t nsl, uint32_t gen, uint32_t* word) {
+  if (c && nsl >= 2) {
+    c->dst = dst; c->src = src; c->per_bytes = per_bytes; c->total_bytes = total_bytes;
+    c->nsl = nsl; c->word_gen = gen; c->word = word;
+    c->main_done = 0; c->helper_done = 0;
+    __atomic_store_n(&c->job_gen, c->job_gen + 1, __ATOMIC_RELEASE);
+    for (uint32_t j = 0; j < nsl; j += 2) {
+      const size_t b = (size_t)j * per_bytes;
+      const size_t e = b + per_bytes < total_bytes ? b + per_bytes : total_bytes;
+      stage_copy_bytes(dst + b, src + b, e - b);
+      __atomic_store_n(&c->main_done, c->main_done + 1, __ATOMIC_RELEASE);
+      publish_prefix(c);
+    }
+    const uint32_t odd = nsl / 2;
+    while (__atomic_load_n(&c->helper_done, __ATOMIC_ACQUIRE) < odd) __builtin_ia32_pause();
+  } else {
+    uint32_t j = 0;
+    for (size_t b = 0; b < total_bytes; b += per_bytes) {
+      const size_t e = b + per_bytes < total_bytes ? b + per_bytes : total_bytes;
+      stage_copy_bytes(dst + b, src + b, e - b);
+      __atomic_store_n(word, (gen << 8) | ++j, __ATOMIC_RELEASE);
+    }
+  }
+}
