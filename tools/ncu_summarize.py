@@ -8,7 +8,9 @@ import collections, csv, io, json, os, re, shutil, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01b"
-G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+G = os.path.join(ROOT, "gpurun_out")
+P = os.environ.get("NCU_SUMMARY_OUT") or os.path.join(ROOT, "profiles")   # on the GPU box: a directory under gpurun_out/
+os.makedirs(P, exist_ok=True)
 
 
 def launch_shares():
