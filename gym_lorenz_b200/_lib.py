@@ -114,6 +114,7 @@ SYMBOLS = [
     ("cl_step_host_wait", C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.POINTER(C.c_int64)]),
     ("cl_step_host_wait_view", C.c_int, [_VP, _VP, C.POINTER(HostView)]),
     ("cl_reset_host", C.c_int, [_VP, _VP, C.POINTER(Buffers), _VP]),
+    ("cl_host_streamed_fallbacks", C.c_int64, [_VP]),
     ("cl_host_h2d_bytes", C.c_int64, [_VP]),
     ("cl_host_d2h_bytes", C.c_int64, [_VP]),
     ("cl_measure_fma_peak", C.c_int, [C.c_int32, C.c_int32, C.c_double, C.POINTER(C.c_double)]),

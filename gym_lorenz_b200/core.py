@@ -403,6 +403,11 @@ class ChaosBatch:
              "streamed": L.HOST_STREAMED}[mode]
         L.check(self.lib.cl_host_set_mode(self.ctx, m, int(slices)), self.ctx, "cl_host_set_mode")
 
+    @property
+    def streamed_fallbacks(self) -> int:
+        """Streamed host steps that were called off and redone as zero-copy steps (synchronous launches)."""
+        return self.lib.cl_host_streamed_fallbacks(self.ctx)
+
     def reset_host(self) -> np.ndarray:
         obs = np.empty((self.num_envs, self.obs_dim), np.float32)
         L.check(self.lib.cl_reset_host(self.ctx, self._host_stream(), C.byref(self._bufs),

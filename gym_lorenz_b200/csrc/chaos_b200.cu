@@ -86,6 +86,8 @@ struct HostStage {
   uint8_t* d_warp_done;  // device copy for CL_HOST_DMA (travels with the result block)
   size_t wd_bytes;
   struct CopyHelper* helper;   // second staging thread (nullptr: single-threaded staging)
+  cl_buffers redo_buf;         // buffers of the step in flight
+  int64_t streamed_fallbacks;  // streamed steps called off by k_relay and redone as zero-copy steps
 };
 
 }  // namespace
@@ -300,10 +302,19 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
 
 __global__ void k_advance_step(uint64_t* step, uint64_t count) { *step += count; }
 
+// Streamed host mode.  Mirrors the pinned "slices staged" word ((gen << 8) | count) into device memory
+// until all `nslices` are published.  It is also the judge of whether streaming works at all: if NOTHING is
+// published within 20 ms of its start, the CPU is evidently not running concurrently with the GPU work
+// (a profiler or CUDA_LAUNCH_BLOCKING made the launches synchronous, so the staging loop only starts after
+// the kernels have finished).  It then writes count 255 = "called off": every block of the step kernel
+// exits before storing anything, *host_err = 2 tells cl_step_host_wait to redo the step from the (by then
+// complete) staging buffer without streaming and to keep this context out of streamed mode.
+// *host_err = 1: published partially and then nothing for 2 s -- unrecoverable, reported as an error.
 __global__ void k_relay(const uint32_t* host_word, uint32_t* dev_word, uint32_t gen, uint32_t nslices, uint32_t* host_err) {
   if (threadIdx.x != 0) return;
   uint32_t last = 0, polls = 0;
   uint64_t t0 = 0, t1 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (;;) {
     const uint32_t v = cl::ld_acquire_sys_u32(host_word);     // one system-scope read per ~4 us: the only one on the GPU
     if ((v >> 8) == gen && (v & 255u) > last) {
@@ -312,10 +323,15 @@ __global__ void k_relay(const uint32_t* host_word, uint32_t* dev_word, uint32_t 
       __threadfence();
       if (last >= nslices) return;
     }
-    if ((++polls & 63u) == 0u) {
+    if ((++polls & 7u) == 0u) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t0 == 0) t0 = t1;
-      if (t1 - t0 > 2000000000ull) { *host_err = 1u; return; }
+      const uint64_t waited = t1 - t0;
+      if ((last == 0 && waited > 20000000ull) || waited > 2000000000ull) {
+        *(volatile uint32_t*)dev_word = (gen << 8) | 255u;
+        __threadfence();
+        *host_err = last == 0 ? 2u : 1u;
+        return;
+      }
     }
   }
 }
@@ -649,17 +665,26 @@ extern "C" int cl_host_action_staging(cl_ctx* ctx, float** act) {
   return CL_OK;
 }
 
+static int host_step_launch(cl_ctx* ctx, cudaStream_t st, const cl_buffers* buf, const float* action_host);
+
 extern "C" int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* buf, const float* action_host) {
   if (!ctx) return fail(nullptr, CL_EINVAL, "null ctx");
   int r = host_stage_init(ctx);
   if (r) return r;
   HostStage& h = ctx->hs;
   if (h.pending) return fail(ctx, CL_EINVAL, "cl_step_host_async called twice without cl_step_host_wait");
+  if (!buf) return fail(ctx, CL_EINVAL, "cl_buffers required");
+  CU(cudaSetDevice(ctx->cfg.device));
+  h.redo_buf = *buf;   // cl_step_host_wait redoes a called-off streamed step from the staging buffer
+  return host_step_launch(ctx, host_stream(ctx, stream), buf, action_host);
+}
+
+static int host_step_launch(cl_ctx* ctx, cudaStream_t st, const cl_buffers* buf, const float* action_host) {
+  HostStage& h = ctx->hs;
+  int r = CL_OK;
   const size_t N = (size_t)ctx->cfg.num_envs;
   const size_t A = (size_t)ctx->lay.act_dim, O = (size_t)ctx->lay.obs_dim;
-  cudaStream_t st = host_stream(ctx, stream);
   const bool stage_copy = action_host && action_host != h.h_act;
-  CU(cudaSetDevice(ctx->cfg.device));
   // graph capture cannot contain CPU-side staging: captured steps read the pinned buffer as it is
   int mode = ((h.mode == CL_HOST_PIPELINED || h.mode == CL_HOST_STREAMED) && ctx->graph_mode) ? CL_HOST_ZEROCOPY : h.mode;
   if (mode == CL_HOST_STREAMED && !stage_copy) mode = CL_HOST_ZEROCOPY;   // the caller wrote the pinned buffer itself
@@ -770,7 +795,23 @@ static int host_wait_common(cl_ctx* ctx, void* stream, int64_t* n_done_out) {
   h.pending = false;
   const size_t N = (size_t)ctx->cfg.num_envs, O = (size_t)ctx->lay.obs_dim;
   HostSlot& s = h.slot[h.cur];
-  if (*h.h_err) { *h.h_err = 0u; return fail(ctx, CL_ECUDA, "streamed host step: a block timed out waiting for its action slice"); }
+  if (*h.h_err) {
+    const uint32_t code = *h.h_err;
+    *h.h_err = 0u;
+    CU(cudaStreamSynchronize(h.side));
+    if (code != 2u) return fail(ctx, CL_ECUDA, "streamed host step: staging stalled for 2 s after a partial publication");
+    // Called off before any block stored anything (k_relay): launches are synchronous here, streaming
+    // cannot work.  Redo the step from the staging buffer (complete by now) as a plain zero-copy step --
+    // same Philox step index, same result slot -- and keep this context out of streamed mode.
+    h.mode = CL_HOST_ZEROCOPY;
+    h.streamed_fallbacks += 1;
+    ctx->step_index -= 1;
+    h.cur = (h.cur + kHostRing - 1) % kHostRing;
+    int r = host_step_launch(ctx, st, &h.redo_buf, nullptr);
+    if (r) return r;
+    CU(cudaStreamSynchronize(st));
+    h.pending = false;
+  }
   // finished episodes: scan the per-env-warp flags (N / 32 bytes, 8 at a time); count the done
   // flags only inside flagged warps
   int64_t nd = 0;
@@ -851,6 +892,8 @@ extern "C" int cl_reset_host(cl_ctx* ctx, void* stream, const cl_buffers* buf, f
   memcpy(obs_host, h.slot[h.cur].obs, N * O * sizeof(float));
   return CL_OK;
 }
+
+extern "C" int64_t cl_host_streamed_fallbacks(const cl_ctx* ctx) { return ctx ? ctx->hs.streamed_fallbacks : 0; }
 
 extern "C" int64_t cl_host_h2d_bytes(const cl_ctx* ctx) {
   return ctx ? ctx->cfg.num_envs * ctx->lay.act_dim * (int64_t)sizeof(float) : 0;

@@ -13,9 +13,10 @@
 // ---- second staging thread ------------------------------------------------------------------
 // A single core copies the caller's action array into pinned memory at 12-16 GB/s (50 us for the 786 KB
 // of 65,536 Lorenz envs): in streamed mode that copy, not PCIe, is what the step waits for.  A helper
-// thread takes every other slice.  It spins (pause) while steps keep coming, naps in 100 us sleeps once
-// the env has been idle for 2 ms, and is joined by cl_destroy.  Off when the process may use fewer than
-// 4 cores, for batches whose actions are under 64 KB, or with CHAOS_B200_COPY_THREADS=1.
+// thread can take every other slice (opt-in: CHAOS_B200_COPY_THREADS=2; measured slower, see
+// copy_helper_start).  It spins (pause) while steps keep coming, naps in 100 us sleeps once the env has
+// been idle for 2 ms, and is joined by cl_destroy.  Never started when the process may use fewer than
+// 4 cores or for batches whose actions are under 64 KB.
 struct CopyHelper {
   pthread_t th;
   bool started;
@@ -68,7 +69,10 @@ static void* copy_helper_main(void* arg) {
 }
 
 static CopyHelper* copy_helper_start(size_t action_bytes) {
-  int threads = 2;
+  // opt-in (CHAOS_B200_COPY_THREADS=2): measured on the GPU box at 65,536 envs, streamed mode, 32 slices:
+  // 80.3 us per step with the stepping thread alone vs 94.6 us with the helper (the spinning helper and the
+  // shared publication word cost more than the halved copy saves)
+  int threads = 1;
   if (const char* ov = getenv("CHAOS_B200_COPY_THREADS")) threads = atoi(ov);
   cpu_set_t set;
   CPU_ZERO(&set);

@@ -515,25 +515,35 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
     // that word into device memory, and every block polls the DEVICE copy: uncached reads of host memory
     // cost ~4 us each and are served one at a time (measured: 1 ms per step when all 256 blocks polled
     // the host word themselves), a device word is an L2 hit.  The state loads above are already in
-    // flight meanwhile.  Bounded wait: after ~2 s the block flags the error for cl_step_host_wait.
+    // flight meanwhile.  If the relay reports that the CPU is not publishing at all (launches made
+    // synchronous by a profiler or CUDA_LAUNCH_BLOCKING: the CPU cannot stage while the kernel runs) every
+    // block leaves before it has stored anything and cl_step_host_wait redoes the step without streaming.
+    __shared__ int s_abort;
     if (threadIdx.x == 0) {
       const uint32_t need = (uint32_t)((i - p.i_begin) / p.act_slice_envs) + 1u;
       const volatile uint32_t* word = p.act_ready;
       uint64_t t0 = 0, t1 = 0;
       uint32_t polls = 0;
+      int ab = 0;
       for (;;) {
         const uint32_t v = *word;
-        if ((v >> 8) == p.act_gen && (v & 255u) >= need) break;
+        if ((v >> 8) == p.act_gen) {
+          const uint32_t cnt = v & 255u;
+          if (cnt == 255u) { ab = 1; break; }   // the relay called the step off (see k_relay): leave without a trace
+          if (cnt >= need) break;
+        }
         __nanosleep(200);
         if ((++polls & 63u) == 0u) {
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
           if (t0 == 0) t0 = t1;
-          if (t1 - t0 > 2000000000ull) { if (p.host_err) *p.host_err = 1u; break; }
+          if (t1 - t0 > 3000000000ull) { if (p.host_err) *p.host_err = 1u; ab = 1; break; }
         }
       }
       __threadfence();   // the relay's device store is ordered after its (system-scope) read of the host word
+      s_abort = ab;
     }
     __syncthreads();
+    if (s_abort) return;   // nothing has been stored yet
   }
 
   // actions are fetched one control interval ahead; this only hides their latency while

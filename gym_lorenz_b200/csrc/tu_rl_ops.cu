@@ -35,7 +35,30 @@ __global__ void __launch_bounds__(256) k_gae(const float* __restrict__ rew, cons
   float last = 0.0f;
   float nnt = __fsub_rn(1.0f, last_done[i]);
   float nv = last_val[i];
-  for (int t = T - 1; t >= 0; --t) {
+  // The recurrence is serial in t, the loads are not: with one thread per env and only 65,536 envs the
+  // kernel was latency-bound (ncu: 87 % long-scoreboard stalls, 3.1 TB/s).  The three input streams of U
+  // consecutive steps are fetched first, then the U recurrence steps run out of registers.
+  constexpr int U = 8;
+  int t = T - 1;
+  for (; t >= U - 1; t -= U) {
+    float r[U], v[U], s[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t o = (int64_t)(t - k) * stride + i;
+      r[k] = rew[o]; v[k] = val[o]; s[k] = starts[o];
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t o = (int64_t)(t - k) * stride + i;
+      const float delta = __fsub_rn(__fadd_rn(r[k], __fmul_rn(__fmul_rn(gamma, nv), nnt)), v[k]);
+      last = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last));
+      adv[o] = last;
+      ret[o] = __fadd_rn(last, v[k]);
+      nnt = __fsub_rn(1.0f, s[k]);
+      nv = v[k];
+    }
+  }
+  for (; t >= 0; --t) {
     const int64_t o = (int64_t)t * stride + i;
     const float v = val[o];
     const float delta = __fsub_rn(__fadd_rn(rew[o], __fmul_rn(__fmul_rn(gamma, nv), nnt)), v);
@@ -64,7 +87,11 @@ __global__ void __launch_bounds__(256) k_moments(const TIN* __restrict__ obs, in
       }
     }
   }
-  const unsigned lane = threadIdx.x & 31u;
+  // warp shuffle -> shared memory -> ONE atomic per block and feature: with an atomic per warp, 9,472 warps
+  // queued on 12 addresses (ncu: 122 us for 25 MB, 91 % long-scoreboard) -- the same-address atomics, not
+  // the reads, set the time
+  __shared__ double sm_part[8][2 * MAXD];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < MAXD; ++c) {
     if (c < dim) {
@@ -74,8 +101,16 @@ __global__ void __launch_bounds__(256) k_moments(const TIN* __restrict__ obs, in
         a += __shfl_xor_sync(0xffffffffu, a, o);
         b += __shfl_xor_sync(0xffffffffu, b, o);
       }
-      if (lane == 0) { atomicAdd(&out[c], a); atomicAdd(&out[dim + c], b); }
+      if (lane == 0) { sm_part[warp][c] = a; sm_part[warp][MAXD + c] = b; }
     }
+  }
+  __syncthreads();
+  const int nwarp = blockDim.x >> 5;
+  for (int k = threadIdx.x; k < 2 * dim; k += blockDim.x) {
+    const int c = k < dim ? k : MAXD + (k - dim);
+    double a = 0.0;
+    for (int w = 0; w < nwarp; ++w) a += sm_part[w][c];
+    atomicAdd(&out[k], a);
   }
 }
 
@@ -89,12 +124,19 @@ __global__ void __launch_bounds__(256) k_normalize(const float* __restrict__ in,
                                                    int dim, const double* __restrict__ mean,
                                                    const double* __restrict__ var, double eps, double clip) {
   extern __shared__ __align__(16) float sm_norm[];   // ROWS: [warps][32 * dim]
+  // sqrt(var + eps) and the mean once per block (was: one f64 sqrt per element; ncu: FP64 + XU pipes 46 %
+  // busy on a kernel that should only stream); the division stays a division, so the result keeps the
+  // exact rounding of (x - mean) / sqrt(var + eps)
+  __shared__ double sm_mean[48], sm_std[48];
+  for (int c = threadIdx.x; c < dim && c < 48; c += blockDim.x) { sm_mean[c] = mean[c]; sm_std[c] = sqrt(var[c] + eps); }
+  __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   float* sm = sm_norm + (threadIdx.x >> 5) * (32 * dim);
   if (i < n) {
     for (int c = 0; c < dim; ++c) {
-      double z = ((double)in[i * ies + c * ics] - mean[c]) / sqrt(var[c] + eps);
+      const double m = c < 48 ? sm_mean[c] : mean[c], sd = c < 48 ? sm_std[c] : sqrt(var[c] + eps);
+      double z = ((double)in[i * ies + c * ics] - m) / sd;
       z = z < -clip ? -clip : (z > clip ? clip : z);
       if (ROWS) sm[lane * dim + c] = (float)z;
       else out[i * oes + c * ocs] = (float)z;
@@ -182,6 +224,52 @@ __global__ void __launch_bounds__(256) k_frame_stack_warp(float* __restrict__ st
   }
 }
 
+// Rows of at most 32 floats (the reference's pipeline: 6 x 4 = 24): one warp owns 32 consecutive rows and
+// walks them row by row with lane j on float j -- a row is one contiguous, sector-aligned piece, the shift
+// by one frame is a warp shuffle, no shared memory and no index arithmetic.  (The general kernel above
+// computes row / column of every float with integer divisions: ncu counted 1,443 instructions per warp,
+// 70 % issue-slot utilisation, 67 us at 1 Mi envs for 200 MB.)
+__global__ void __launch_bounds__(256) k_frame_stack_row32(float* __restrict__ stacked, const float* __restrict__ obs,
+                                                           int64_t es, int64_t cs, const uint8_t* __restrict__ done,
+                                                           const float* __restrict__ term_in, int64_t tes, int64_t tcs,
+                                                           float* __restrict__ term_out, int64_t n, int dim, int k) {
+  const unsigned lane = threadIdx.x & 31u;
+  const int rowlen = dim * k, keep = rowlen - dim;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
+  if (row0 >= n) return;
+  const int rows = (int)(n - row0 >= 32 ? 32 : n - row0);
+  const bool in_row = (int)lane < rowlen, is_new = in_row && (int)lane >= keep;
+  const int c_new = (int)lane - keep;
+  // done flags of the warp's 32 rows: one coalesced byte load, then a ballot
+  const bool d_mine = (int)lane < rows && done != nullptr && done[row0 + lane] != 0;
+  const unsigned done_mask = __ballot_sync(0xffffffffu, d_mine);
+  float old_v[4], new_v[4];
+#pragma unroll 1
+  for (int r0 = 0; r0 < rows; r0 += 4) {          // 4 rows in flight per iteration
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      const bool ok = r < rows;
+      float* row = stacked + (row0 + r) * rowlen;
+      old_v[u] = (ok && in_row) ? row[lane] : 0.0f;
+      new_v[u] = (ok && is_new) ? obs[(row0 + r) * es + c_new * cs] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = r0 + u;
+      if (r >= rows) break;
+      float* row = stacked + (row0 + r) * rowlen;
+      const float shifted = __shfl_down_sync(0xffffffffu, old_v[u], dim);     // old[j + dim]
+      const bool d = (done_mask >> r) & 1u;
+      if (d && term_out != nullptr && in_row) {
+        const float tv = is_new ? term_in[(row0 + r) * tes + c_new * tcs] : shifted;
+        term_out[(row0 + r) * rowlen + lane] = tv;
+      }
+      if (in_row) row[lane] = is_new ? new_v[u] : (d ? 0.0f : shifted);
+    }
+  }
+}
+
 // fallback for very long rows (shared memory): one thread per row
 __global__ void __launch_bounds__(256) k_frame_stack(float* __restrict__ stacked, const float* __restrict__ obs,
                                                      int64_t es, int64_t cs, const uint8_t* __restrict__ done,
@@ -210,18 +298,40 @@ __global__ void __launch_bounds__(256) k_eval_metrics(const double* __restrict__
   if (i >= n) return;
   double sa[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, en = 0.0;
   int last_ex[4] = {-1, -1, -1, -1};
-  for (int t = 0; t < T; ++t) {
+  // One thread per trajectory walks T steps; with a few thousand trajectories there are too few threads to
+  // cover the memory latency one step at a time (ncu: 85 % long-scoreboard, 382 GB/s).  The loads of U
+  // consecutive steps are issued together, the sums then run in the reference's order (t ascending).
+  constexpr int U = 4;
+  auto step = [&](int t, const double* e, const double* a) {
     for (int c = 0; c < ncomp; ++c) {
-      const double e = err[((int64_t)t * ncomp + c) * stride + i];
-      if (fabs(e) > band) last_ex[c] = t;
-      if (t >= steady_start) { sa[c] += fabs(e); sq[c] += e * e; }
+      if (fabs(e[c]) > band) last_ex[c] = t;
+      if (t >= steady_start) { sa[c] += fabs(e[c]); sq[c] += e[c] * e[c]; }
     }
     double q = 0.0;
-    for (int c = 0; c < nctrl; ++c) {
-      const double a = u[((int64_t)t * nctrl + c) * stride + i];
-      q += a * a;
-    }
+    for (int c = 0; c < nctrl; ++c) q += a[c] * a[c];
     en += q;
+  };
+  int t = 0;
+  for (; t + U <= T; t += U) {
+    double e[U][4], a[U][4];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        e[k][c] = c < ncomp ? err[((int64_t)(t + k) * ncomp + c) * stride + i] : 0.0;
+        a[k][c] = c < nctrl ? u[((int64_t)(t + k) * nctrl + c) * stride + i] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) step(t + k, e[k], a[k]);
+  }
+  for (; t < T; ++t) {
+    double e[4], a[4];
+    for (int c = 0; c < 4; ++c) {
+      e[c] = c < ncomp ? err[((int64_t)t * ncomp + c) * stride + i] : 0.0;
+      a[c] = c < nctrl ? u[((int64_t)t * nctrl + c) * stride + i] : 0.0;
+    }
+    step(t, e, a);
   }
   const double m = (double)(T - steady_start);
   double mae = 0.0, rmse = 0.0, ts = -1.0;
@@ -264,7 +374,7 @@ extern "C" int cl_obs_moments(void* stream, const float* obs, int64_t es, int64_
   if (e != cudaSuccess) return CL_ECUDA;
   const int block = 256;
   int64_t blocks = (n + block - 1) / block;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   if (dim <= 8) k_moments<8, float><<<(unsigned)blocks, block, 0, st>>>(obs, es, cs, n, dim, shift, out2d);
   else k_moments<32, float><<<(unsigned)blocks, block, 0, st>>>(obs, es, cs, n, dim, shift, out2d);
   return fail_if(cudaGetLastError());
@@ -279,7 +389,7 @@ extern "C" int cl_moments_f64(void* stream, const double* x, int64_t es, int64_t
   if (e != cudaSuccess) return CL_ECUDA;
   const int block = 256;
   int64_t blocks = (n + block - 1) / block;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   if (dim <= 8) k_moments<8, double><<<(unsigned)blocks, block, 0, st>>>(x, es, cs, n, dim, shift, out2d);
   else k_moments<32, double><<<(unsigned)blocks, block, 0, st>>>(x, es, cs, n, dim, shift, out2d);
   return fail_if(cudaGetLastError());
@@ -336,7 +446,11 @@ static int frame_stack_launch(cudaStream_t st, float* stacked, const float* obs,
                               int64_t n, int32_t dim, int32_t n_stack) {
   const int block = 256, wpb = block / 32;
   const size_t smem = (size_t)wpb * (32 * (size_t)dim * n_stack + 64 * (size_t)dim) * sizeof(float);
-  if (smem <= 48 * 1024) {
+  if (dim * n_stack <= 32) {
+    const int64_t warps = (n + 31) / 32;
+    k_frame_stack_row32<<<(unsigned)((warps + wpb - 1) / wpb), block, 0, st>>>(stacked, obs, es, cs, done, term_in, tes,
+                                                                                tcs, term_out, n, dim, n_stack);
+  } else if (smem <= 48 * 1024) {
     const int64_t warps = (n + 31) / 32;
     k_frame_stack_warp<<<(unsigned)((warps + wpb - 1) / wpb), block, smem, st>>>(stacked, obs, es, cs, done, term_in, tes,
                                                                                  tcs, term_out, n, dim, n_stack);
@@ -364,7 +478,7 @@ extern "C" int cl_frame_stack_term(void* stream, float* stacked, const float* ob
 extern "C" int cl_eval_metrics(void* stream, const double* err, const double* ctrl, int32_t T, int32_t n_err,
                                int32_t n_ctrl, int64_t n, int64_t stride, int32_t steady_start, double dt,
                                double error_band, double* out4) {
-  if (!err || !ctrl || !out4 || T < 1 || n_err < 1 || n_err > 4 || n_ctrl < 0 || n < 1 || steady_start < 0 ||
+  if (!err || !ctrl || !out4 || T < 1 || n_err < 1 || n_err > 4 || n_ctrl < 0 || n_ctrl > 4 || n < 1 || steady_start < 0 ||
       steady_start >= T)
     return CL_EINVAL;
   const int block = 128;

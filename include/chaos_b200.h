@@ -258,6 +258,10 @@ int cl_host_set_zero_copy(cl_ctx* ctx, int enable);
  * Results are identical in all modes (same kernel, same per-env Philox streams). */
 enum { CL_HOST_DMA = 0, CL_HOST_ZEROCOPY = 1, CL_HOST_PIPELINED = 2, CL_HOST_STREAMED = 3 };
 int cl_host_set_mode(cl_ctx* ctx, int mode, int slices);
+/* streamed steps that were called off and redone as zero-copy steps because the CPU could not stage while
+ * the kernel ran (synchronous launches: profilers, CUDA_LAUNCH_BLOCKING); after the first one the context
+ * stays in zero-copy mode */
+int64_t cl_host_streamed_fallbacks(const cl_ctx* ctx);
 int cl_step_host_async(cl_ctx* ctx, void* stream, const cl_buffers* buf, const float* action_host);
 int cl_step_host_wait(cl_ctx* ctx, void* stream, float* obs_host, float* reward_host,
                       uint8_t* done_host, float* term_obs_host, double* last_ep_ret_host,

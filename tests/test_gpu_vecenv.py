@@ -344,3 +344,39 @@ def test_tensor_path_has_no_host_round_trip():
     assert copies == [], copies
     assert bool(torch.isfinite(ret).all())
     env.close()
+
+
+def test_streamed_host_mode_survives_synchronous_launches(tmp_path):
+    """With CUDA_LAUNCH_BLOCKING=1 (or under a profiler) a launch returns only when the kernel has finished,
+    so the CPU cannot stage the action array while the step kernel runs.  The relay kernel notices that
+    nothing is published, calls the step off before any block has stored anything, and step_wait redoes it
+    as a zero-copy step: same results as zero-copy mode, one fallback recorded, later steps not streamed."""
+    import json
+    import subprocess
+    import sys
+    script = tmp_path / "run.py"
+    script.write_text(
+        "import sys, json, hashlib\n"
+        f"sys.path.insert(0, {str(H.os.path.dirname(H.os.path.dirname(H.os.path.abspath(__file__))))!r})\n"
+        "import numpy as np\n"
+        "from gym_lorenz_b200.vec_env import BatchedChaosVecEnv\n"
+        "mode = sys.argv[1]\n"
+        "env = BatchedChaosVecEnv('hr_sync', 20000, seed=3, max_episode_steps=4)\n"
+        "env.batch.set_host_mode(mode, 8)\n"
+        "env.reset()\n"
+        "rng = np.random.default_rng(1)\n"
+        "h = hashlib.sha256()\n"
+        "for t in range(6):\n"
+        "    obs, rew, done, infos = env.step(rng.uniform(-1, 1, (20000, 2)).astype(np.float32))\n"
+        "    h.update(obs.tobytes()); h.update(rew.tobytes()); h.update(done.tobytes())\n"
+        "print(json.dumps({'hash': h.hexdigest(), 'fallbacks': int(env.batch.streamed_fallbacks)}))\n")
+    out = {}
+    for mode, blocking in (("zerocopy", "0"), ("streamed", "0"), ("streamed", "1")):
+        env = dict(H.os.environ, CUDA_LAUNCH_BLOCKING=blocking)
+        r = subprocess.run([sys.executable, str(script), mode], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[(mode, blocking)] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out[("streamed", "0")]["hash"] == out[("zerocopy", "0")]["hash"]
+    assert out[("streamed", "1")]["hash"] == out[("zerocopy", "0")]["hash"]
+    assert out[("streamed", "0")]["fallbacks"] == 0
+    assert out[("streamed", "1")]["fallbacks"] == 1
