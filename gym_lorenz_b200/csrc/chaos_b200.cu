@@ -577,16 +577,21 @@ extern "C" int cl_block_size(const cl_ctx* ctx) { return ctx ? ctx->block : 0; }
 
 // ---- host-buffer path ------------------------------------------------------------------
 
-// Default data-movement mode of the host path per (env kind, batch size), from the measured table in
-// profiles/r02_e2e_host_modes.jsonl (tools/e2e_modes.py: lorenz_rk4 / hr_sync / pmsm_sync x {4,096, 65,536}
-// envs x every mode, fresh caller-owned action array each step).  At 65,536 envs: lorenz_rk4 113 (zero-copy)
-// -> 88 us (streamed, 16 slices), pmsm_sync 91 -> 76, hr_sync 138 -> 123 (DMA chain: 137 / 113 / 147); at
-// 4,096 envs all within 2 us of each other.  The kind does not change the ranking, so it does not enter.
+// Default data-movement mode of the host path per (env kind, batch size), from the measured table
+// profiles/r02_e2e_host_modes.jsonl (tools/e2e_modes.py: lorenz_rk4 / hr_sync / pmsm_sync x {4,096, 16,384,
+// 65,536} envs x {DMA chain, zero-copy, streamed 8 / 32 slices}, a caller-owned action array each step).
+// What decides is the size of the action array (kind enters through its action dimension): the DMA chain
+// never wins, streamed wins once the staging copy is long enough to hide a relay launch behind.
 static void host_mode_default(int kind, int64_t n, int* mode, int* slices) {
-  (void)kind;
-  *mode = CL_HOST_STREAMED;            // never slower than ZEROCOPY in the table, 10-25 % faster from 16,384 envs up
-  int k = (int)(n / 2048);             // finer slices keep paying up to the relay's poll period (~4 us of staging)
-  *slices = k < 1 ? 1 : (k > 64 ? 64 : k);
+  const int64_t action_bytes = n * (int64_t)kLayouts[kind].act_dim * 4;
+  if (action_bytes >= 384 * 1024) {
+    *mode = CL_HOST_STREAMED;          // 65,536 envs: 94-99 vs 118 us (lorenz_rk4), 83-85 vs 95 (pmsm_sync), 137-139 vs 150 (hr_sync)
+    int k = (int)(n / 2048);           // finer slices keep paying up to the relay's poll period (~4 us of staging)
+    *slices = k < 1 ? 1 : (k > 64 ? 64 : k);
+  } else {
+    *mode = CL_HOST_ZEROCOPY;          // 4,096 / 16,384 envs: the relay launch costs more (2-6 us) than the overlap returns
+    *slices = 1;
+  }
 }
 
 static int host_stage_init(cl_ctx* ctx) {

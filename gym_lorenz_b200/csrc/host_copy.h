@@ -13,8 +13,7 @@
 // ---- second staging thread ------------------------------------------------------------------
 // A single core copies the caller's action array into pinned memory at 12-16 GB/s (50 us for the 786 KB
 // of 65,536 Lorenz envs): in streamed mode that copy, not PCIe, is what the step waits for.  A helper
-// thread can take every other slice (opt-in: CHAOS_B200_COPY_THREADS=2; measured slower, see
-// copy_helper_start).  It spins (pause) while steps keep coming, naps in 100 us sleeps once the env has
+// thread can take the upper half of the slices (CHAOS_B200_COPY_THREADS=2, see copy_helper_start).  It spins (pause) while steps keep coming, naps in 100 us sleeps once the env has
 // been idle for 2 ms, and is joined by cl_destroy.  Never started when the process may use fewer than
 // 4 cores or for batches whose actions are under 64 KB.
 struct CopyHelper {
@@ -22,27 +21,15 @@ struct CopyHelper {
   bool started;
   volatile uint32_t job_gen;     // bumped by the stepping thread to start a job
   volatile uint32_t quit;
-  // job (written before job_gen, read after): odd slices of [0, nsl)
+  // job (written before job_gen, read after): slices [first_helper_slice, nsl) as one piece
   unsigned char* dst;
   const unsigned char* src;
   size_t per_bytes, total_bytes;
-  uint32_t nsl, word_gen;
-  volatile uint32_t main_done, helper_done;   // slices finished by each thread
-  uint32_t* word;                // pinned "slices staged" word, advanced monotonically by both threads
+  uint32_t first_helper_slice;
+  volatile uint32_t helper_done;   // 1 once the helper's piece is staged
 };
 
 static void stage_copy_bytes(void* dst, const void* src, size_t n);
-
-// contiguous prefix of staged slices: evens < 2m done by the stepping thread, odds < 2k + ... by the helper
-static void publish_prefix(CopyHelper* c) {
-  const uint32_t m = c->main_done, k = c->helper_done;
-  uint32_t p = (m <= k) ? 2 * m : 2 * k + 1;
-  if (p > c->nsl) p = c->nsl;
-  const uint32_t want = (c->word_gen << 8) | p;
-  uint32_t cur = __atomic_load_n(c->word, __ATOMIC_RELAXED);
-  while ((cur >> 8) == c->word_gen && (cur & 255u) < p &&
-         !__atomic_compare_exchange_n(c->word, &cur, want, false, __ATOMIC_RELEASE, __ATOMIC_RELAXED)) {}
-}
 
 static void* copy_helper_main(void* arg) {
   CopyHelper* c = (CopyHelper*)arg;
@@ -57,12 +44,10 @@ static void* copy_helper_main(void* arg) {
     }
     seen = g;
     idle = 0;
-    for (uint32_t j = 1; j < c->nsl; j += 2) {
-      const size_t b = (size_t)j * c->per_bytes;
-      const size_t e = b + c->per_bytes < c->total_bytes ? b + c->per_bytes : c->total_bytes;
-      stage_copy_bytes(c->dst + b, c->src + b, e - b);
-      __atomic_store_n(&c->helper_done, c->helper_done + 1, __ATOMIC_RELEASE);
-      publish_prefix(c);
+    {   // the upper half of the slices in one piece; reported once (no shared traffic while copying)
+      const size_t b = (size_t)c->first_helper_slice * c->per_bytes;
+      if (b < c->total_bytes) stage_copy_bytes(c->dst + b, c->src + b, c->total_bytes - b);
+      __atomic_store_n(&c->helper_done, 1u, __ATOMIC_RELEASE);
     }
   }
   return nullptr;
@@ -135,19 +120,19 @@ static void stage_copy_bytes(void* dst, const void* src, size_t n) {
 static void stage_slices(CopyHelper* c, unsigned char* dst, const unsigned char* src, size_t per_bytes,
                          size_t total_bytes, uint32_t nsl, uint32_t gen, uint32_t* word) {
   if (c && nsl >= 2) {
+    // lower half here, slice by slice with publication (its blocks start while the copy goes on); upper
+    // half on the helper in one piece; the full count is published once both are done
+    const uint32_t half = nsl / 2;
     c->dst = dst; c->src = src; c->per_bytes = per_bytes; c->total_bytes = total_bytes;
-    c->nsl = nsl; c->word_gen = gen; c->word = word;
-    c->main_done = 0; c->helper_done = 0;
+    c->first_helper_slice = half; c->helper_done = 0;
     __atomic_store_n(&c->job_gen, c->job_gen + 1, __ATOMIC_RELEASE);
-    for (uint32_t j = 0; j < nsl; j += 2) {
+    for (uint32_t j = 0; j < half; ++j) {
       const size_t b = (size_t)j * per_bytes;
-      const size_t e = b + per_bytes < total_bytes ? b + per_bytes : total_bytes;
-      stage_copy_bytes(dst + b, src + b, e - b);
-      __atomic_store_n(&c->main_done, c->main_done + 1, __ATOMIC_RELEASE);
-      publish_prefix(c);
+      stage_copy_bytes(dst + b, src + b, per_bytes);
+      __atomic_store_n(word, (gen << 8) | (j + 1), __ATOMIC_RELEASE);
     }
-    const uint32_t odd = nsl / 2;
-    while (__atomic_load_n(&c->helper_done, __ATOMIC_ACQUIRE) < odd) __builtin_ia32_pause();
+    while (!__atomic_load_n(&c->helper_done, __ATOMIC_ACQUIRE)) __builtin_ia32_pause();
+    __atomic_store_n(word, (gen << 8) | nsl, __ATOMIC_RELEASE);
   } else {
     uint32_t j = 0;
     for (size_t b = 0; b < total_bytes; b += per_bytes) {

@@ -199,20 +199,31 @@ __global__ void __launch_bounds__(256) k_frame_stack_warp(float* __restrict__ st
   }
   __syncwarp();
   const unsigned done_mask = any_done;
-  auto new_val = [&](int q) -> float {
-    const int r = q / rowlen, j = q - r * rowlen;
+  // (row, column) of a float of the run advance incrementally -- per 128 floats by (128 / rowlen,
+  // 128 % rowlen) -- instead of two integer divisions per float (ncu on the first version: 1,443
+  // instructions per warp, issue slots 70 % busy on a kernel that should only stream)
+  auto val_at = [&](int q, int r, int j) -> float {
     if (j >= keep) return sm_obs[r * dim + (j - keep)];
     return ((done_mask >> r) & 1u) ? 0.0f : sm_old[q + dim];
   };
+  const int dr = 128 / rowlen, dj = 128 % rowlen;
   if (vec) {
-    for (int q = (int)lane * 4; q + 3 < nflt; q += 128) {
-      float4 v;
-      v.x = new_val(q); v.y = new_val(q + 1); v.z = new_val(q + 2); v.w = new_val(q + 3);
-      *reinterpret_cast<float4*>(run + q) = v;
+    int q = (int)lane * 4, r = q / rowlen, j = q - r * rowlen;
+    for (; q + 3 < nflt; q += 128) {
+      float v[4];
+      int rr = r, jj = j;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[e] = val_at(q + e, rr, jj);
+        if (++jj == rowlen) { jj = 0; ++rr; }
+      }
+      *reinterpret_cast<float4*>(run + q) = make_float4(v[0], v[1], v[2], v[3]);
+      r += dr; j += dj;
+      if (j >= rowlen) { j -= rowlen; ++r; }
     }
-    for (int q = (nflt & ~3) + (int)lane; q < nflt; q += 32) run[q] = new_val(q);
+    for (int q2 = (nflt & ~3) + (int)lane; q2 < nflt; q2 += 32) { const int r2 = q2 / rowlen; run[q2] = val_at(q2, r2, q2 - r2 * rowlen); }
   } else {
-    for (int q = (int)lane; q < nflt; q += 32) run[q] = new_val(q);
+    for (int q2 = (int)lane; q2 < nflt; q2 += 32) { const int r2 = q2 / rowlen; run[q2] = val_at(q2, r2, q2 - r2 * rowlen); }
   }
   if (term_out != nullptr && any_done) {
     // rows of envs that did not finish are not meaningful and never read (same convention as term_obs)
@@ -220,52 +231,6 @@ __global__ void __launch_bounds__(256) k_frame_stack_warp(float* __restrict__ st
     for (int q = (int)lane; q < nflt; q += 32) {
       const int r = q / rowlen, j = q - r * rowlen;
       trun[q] = j >= keep ? sm_term[r * dim + (j - keep)] : sm_old[q + dim];
-    }
-  }
-}
-
-// Rows of at most 32 floats (the reference's pipeline: 6 x 4 = 24): one warp owns 32 consecutive rows and
-// walks them row by row with lane j on float j -- a row is one contiguous, sector-aligned piece, the shift
-// by one frame is a warp shuffle, no shared memory and no index arithmetic.  (The general kernel above
-// computes row / column of every float with integer divisions: ncu counted 1,443 instructions per warp,
-// 70 % issue-slot utilisation, 67 us at 1 Mi envs for 200 MB.)
-__global__ void __launch_bounds__(256) k_frame_stack_row32(float* __restrict__ stacked, const float* __restrict__ obs,
-                                                           int64_t es, int64_t cs, const uint8_t* __restrict__ done,
-                                                           const float* __restrict__ term_in, int64_t tes, int64_t tcs,
-                                                           float* __restrict__ term_out, int64_t n, int dim, int k) {
-  const unsigned lane = threadIdx.x & 31u;
-  const int rowlen = dim * k, keep = rowlen - dim;
-  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
-  if (row0 >= n) return;
-  const int rows = (int)(n - row0 >= 32 ? 32 : n - row0);
-  const bool in_row = (int)lane < rowlen, is_new = in_row && (int)lane >= keep;
-  const int c_new = (int)lane - keep;
-  // done flags of the warp's 32 rows: one coalesced byte load, then a ballot
-  const bool d_mine = (int)lane < rows && done != nullptr && done[row0 + lane] != 0;
-  const unsigned done_mask = __ballot_sync(0xffffffffu, d_mine);
-  float old_v[4], new_v[4];
-#pragma unroll 1
-  for (int r0 = 0; r0 < rows; r0 += 4) {          // 4 rows in flight per iteration
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int r = r0 + u;
-      const bool ok = r < rows;
-      float* row = stacked + (row0 + r) * rowlen;
-      old_v[u] = (ok && in_row) ? row[lane] : 0.0f;
-      new_v[u] = (ok && is_new) ? obs[(row0 + r) * es + c_new * cs] : 0.0f;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int r = r0 + u;
-      if (r >= rows) break;
-      float* row = stacked + (row0 + r) * rowlen;
-      const float shifted = __shfl_down_sync(0xffffffffu, old_v[u], dim);     // old[j + dim]
-      const bool d = (done_mask >> r) & 1u;
-      if (d && term_out != nullptr && in_row) {
-        const float tv = is_new ? term_in[(row0 + r) * tes + c_new * tcs] : shifted;
-        term_out[(row0 + r) * rowlen + lane] = tv;
-      }
-      if (in_row) row[lane] = is_new ? new_v[u] : (d ? 0.0f : shifted);
     }
   }
 }
@@ -301,7 +266,7 @@ __global__ void __launch_bounds__(256) k_eval_metrics(const double* __restrict__
   // One thread per trajectory walks T steps; with a few thousand trajectories there are too few threads to
   // cover the memory latency one step at a time (ncu: 85 % long-scoreboard, 382 GB/s).  The loads of U
   // consecutive steps are issued together, the sums then run in the reference's order (t ascending).
-  constexpr int U = 4;
+  constexpr int U = 8;
   auto step = [&](int t, const double* e, const double* a) {
     for (int c = 0; c < ncomp; ++c) {
       if (fabs(e[c]) > band) last_ex[c] = t;
@@ -446,11 +411,7 @@ static int frame_stack_launch(cudaStream_t st, float* stacked, const float* obs,
                               int64_t n, int32_t dim, int32_t n_stack) {
   const int block = 256, wpb = block / 32;
   const size_t smem = (size_t)wpb * (32 * (size_t)dim * n_stack + 64 * (size_t)dim) * sizeof(float);
-  if (dim * n_stack <= 32) {
-    const int64_t warps = (n + 31) / 32;
-    k_frame_stack_row32<<<(unsigned)((warps + wpb - 1) / wpb), block, 0, st>>>(stacked, obs, es, cs, done, term_in, tes,
-                                                                                tcs, term_out, n, dim, n_stack);
-  } else if (smem <= 48 * 1024) {
+  if (smem <= 48 * 1024) {
     const int64_t warps = (n + 31) / 32;
     k_frame_stack_warp<<<(unsigned)((warps + wpb - 1) / wpb), block, smem, st>>>(stacked, obs, es, cs, done, term_in, tes,
                                                                                  tcs, term_out, n, dim, n_stack);

@@ -16,7 +16,10 @@ for N in sizes:
     env.reset()
     b = env.batch
     rng = np.random.default_rng(0)
-    acts = [rng.uniform(-1, 1, (N, b.act_dim)).astype(np.float32) for _ in range(4)]
+    # 4 rotating arrays stay warm in the CPU caches (a policy that has just written its output); E2E_ARRAYS=16
+    # makes the source cold (L3 / DRAM)
+    n_arr = int(os.environ.get("E2E_ARRAYS", "4"))
+    acts = [rng.uniform(-1, 1, (N, b.act_dim)).astype(np.float32) for _ in range(n_arr)]
     pin = b.host_action_buffer(); pin[:] = acts[0]
 
     def bench(fn, n=300):
@@ -31,6 +34,7 @@ for N in sizes:
         b.set_host_mode(mode, s)
         row = {"kind": kind, "envs": N, "mode": mode, "slices": s,
                "us_pinned_actions": round(bench(pinned), 2),
-               "us_ndarray_actions": round(bench(lambda k: env.step(acts[k % 4])), 2)}
+               "us_ndarray_actions": round(bench(lambda k: env.step(acts[k % n_arr])), 2), "arrays": n_arr,
+               "copy_threads": int(os.environ.get("CHAOS_B200_COPY_THREADS", "1"))}
         print(json.dumps(row), flush=True)
     env.close()
