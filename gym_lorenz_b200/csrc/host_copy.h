@@ -54,10 +54,12 @@ static void* copy_helper_main(void* arg) {
 }
 
 static CopyHelper* copy_helper_start(size_t action_bytes) {
-  // opt-in (CHAOS_B200_COPY_THREADS=2): measured on the GPU box at 65,536 envs, streamed mode, 32 slices:
-  // 80.3 us per step with the stepping thread alone vs 94.6 us with the helper (the spinning helper and the
-  // shared publication word cost more than the halved copy saves)
-  int threads = 1;
+  // Measured on the GPU box at 65,536 envs, streamed mode, 32 slices (profiles/r02_e2e_copy_threads.jsonl):
+  // lorenz_rk4 94.9 -> 83.1 us per step with a warm source array, 97.0 -> 84.3 us with a cold one; hr_sync
+  // 100.5 -> 93.5 / 88.1 -> 82.4.  (A first version that interleaved the two threads slice by slice and
+  // had both advance the publication word was SLOWER than one thread: 94.6 vs 80.3 us.)
+  // CHAOS_B200_COPY_THREADS=1 turns the helper off.
+  int threads = 2;
   if (const char* ov = getenv("CHAOS_B200_COPY_THREADS")) threads = atoi(ov);
   cpu_set_t set;
   CPU_ZERO(&set);
