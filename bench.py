@@ -326,8 +326,8 @@ def run_b200(args):
         except Exception:  # noqa: BLE001
             pass
         roofline = {
-            "kernel": (f"cl::k_rollout_sm<{ENV_TYPE[args.kind]}> (fused T-interval rollout, per-SM queue of env-warp x chunk "
-                       f"tasks, env state in shared memory)" if sm_local
+            "kernel": (f"cl::k_rollout_sm<{ENV_TYPE[args.kind]}> (fused T-interval rollout; per SM: resident env-warps in registers, "
+                       f"guest env-warps chunked through a shared-memory queue, actions by tensor copies)" if sm_local
                        else f"cl::k_rollout_dyn<{ENV_TYPE[args.kind]}{plain}> (fused T-interval rollout, env-warp x chunk tasks)" if dyn
                        else f"cl::k_step<{ENV_TYPE[args.kind]}, ROLL=true{plain}> (fused T-interval rollout)"),
             "bound": "fp64" if fma_bytes == 8 else "fp32", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
