@@ -140,13 +140,17 @@ static bool is_parity(int kind) { return !(kind >= CL_ENV_LORENZ_RK4 && kind <= 
 // SMs: 64-thread blocks give 7 x 64 = 448 threads on the fullest SM vs 512 for 128 / 256.
 static int pick_block(int64_t n, int sms) {
   const int cand[3] = {64, 128, 256};
-  int best = 256;
-  int64_t best_cost = -1;
+  int64_t cost[3], best_cost = -1;
   for (int k = 0; k < 3; ++k) {
     const int64_t blocks = (n + cand[k] - 1) / cand[k];
-    const int64_t cost = ((blocks + sms - 1) / sms) * cand[k];
-    if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = cand[k]; }
+    cost[k] = ((blocks + sms - 1) / sms) * cand[k];
+    if (best_cost < 0 || cost[k] < best_cost) best_cost = cost[k];
   }
+  // the largest block within 1.5 % of the best balance: per-block work (the episode-statistics flush, the
+  // streamed mode's flag poll) is then shared by more envs -- at 1 Mi envs all three sizes are within 1 %
+  int best = 64;
+  for (int k = 0; k < 3; ++k)
+    if (cost[k] * 1000 <= best_cost * 1015) best = cand[k];
   return best;
 }
 

@@ -342,7 +342,7 @@ __device__ __forceinline__ unsigned env_interval(typename E::S& s, int32_t& ep_l
                                              const unsigned lane, const int t, const uint64_t step,
                                              const float* a, const bool want_noise, const bool obs64,
                                              const bool autoreset, unsigned& bad_acc, float* sm_rows, bool& fin,
-                                             PlainPending<E>* pend = nullptr) {
+                                             PlainPending<E>* pend = nullptr, double* blk_stats = nullptr) {
   typedef typename E::real real;
   if (PLAIN && CL_PLAIN_DEFER) plain_emit<E, RUNPTR>(p, i, live, *pend);   // outputs of the previous interval
   // The per-interval Philox stream (key / counter words).  Generic kernels build it up front: building
@@ -394,12 +394,16 @@ __device__ __forceinline__ unsigned env_interval(typename E::S& s, int32_t& ep_l
     const unsigned tm = __ballot_sync(0xffffffffu, mine && term);
     const unsigned um = __ballot_sync(0xffffffffu, mine && trunc && !term);
     if (lane == 0) {
-      atomicAdd(&p.stats[CL_STAT_EPISODES], (double)__popc(dm));
-      atomicAdd(&p.stats[CL_STAT_RET_SUM], r1);
-      atomicAdd(&p.stats[CL_STAT_RET_SQ], r2);
-      atomicAdd(&p.stats[CL_STAT_LEN_SUM], (double)l1);
-      if (tm) atomicAdd(&p.stats[CL_STAT_TERMINATED], (double)__popc(tm));
-      if (um) atomicAdd(&p.stats[CL_STAT_TRUNCATED], (double)__popc(um));
+      // blk_stats: block-shared accumulator of k_step (flushed once per block).  With a global atomic per
+      // warp, a batch in which most env-warps end an episode every step (memristive pair under full-range
+      // forcing at 1 Mi envs: 32,768 warps x 6 atomics on 6 addresses) spends half its time queueing there.
+      double* dst = blk_stats != nullptr ? blk_stats : p.stats;
+      atomicAdd(&dst[CL_STAT_EPISODES], (double)__popc(dm));
+      atomicAdd(&dst[CL_STAT_RET_SUM], r1);
+      atomicAdd(&dst[CL_STAT_RET_SQ], r2);
+      atomicAdd(&dst[CL_STAT_LEN_SUM], (double)l1);
+      if (tm) atomicAdd(&dst[CL_STAT_TERMINATED], (double)__popc(tm));
+      if (um) atomicAdd(&dst[CL_STAT_TRUNCATED], (double)__popc(um));
     }
   }
   bad_acc += __popc(bm);  // flushed once per launch / task (diverged envs would otherwise
@@ -489,6 +493,9 @@ template <class E> struct StepMinBlocks { enum { value = 0 }; };
 template <class E, bool ROLL, bool PLAIN = false>
 __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_step(const KParams p) {
   extern __shared__ __align__(16) float sm_rows_all[];  // [warps per block][32 * OBS], row-store staging
+  __shared__ double s_stats[CL_NSTATS];                  // episode statistics of this block
+  if (threadIdx.x < CL_NSTATS) s_stats[threadIdx.x] = 0.0;
+  __syncthreads();
   const int64_t i = p.i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < p.n;
   const unsigned lane = threadIdx.x & 31u;
@@ -579,7 +586,7 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
             a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
         }
       }
-      const unsigned dall = env_interval<E, ROLL, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin, &pend);
+      const unsigned dall = env_interval<E, ROLL, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin, &pend, s_stats);
       if (!ROLL && !PLAIN && p.warp_done != nullptr && dall && lane == 0) p.warp_done[i >> 5] = 1;
     }
   };
@@ -590,12 +597,14 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
   } else {
     intervals(SpecTag<0>{});
   }
-  if (bad_acc && lane == 0) atomicAdd(&p.stats[CL_STAT_NONFINITE], (double)bad_acc);
+  if (bad_acc && lane == 0) atomicAdd(&s_stats[CL_STAT_NONFINITE], (double)bad_acc);
   if (live) {
     E::store(s, p, i);
     p.ep_len[i] = ep_len;
     p.ep_return[i] = ep_ret;
   }
+  __syncthreads();
+  if (threadIdx.x < CL_NSTATS && s_stats[threadIdx.x] != 0.0) atomicAdd(&p.stats[threadIdx.x], s_stats[threadIdx.x]);
 }
 
 // ---- the dynamic rollout kernel ---------------------------------------------------------

@@ -78,7 +78,13 @@ struct Stream {
 // 53-bit uniform in [0,1): same construction as NumPy's random_double
 // ((a >> 5) * 2^26 + (b >> 6)) / 2^53, from two 32-bit words.
 CL_HD double u01_53(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  // the same 53-bit integer assembled from two exact 32-bit conversions ((a >> 5) * 2^26 + (b >> 6) < 2^53 is
+  // exact in double): a 64-bit integer -> double conversion is a multi-instruction sequence on the GPU
+  return __fma_rn((double)(a >> 5), 67108864.0, (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+#else
   return (double)(((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6)) * (1.0 / 9007199254740992.0);
+#endif
 }
 
 // uniform(lo, hi) as NumPy evaluates it: lo + (hi - lo) * u  (two roundings, no FMA).
