@@ -139,18 +139,16 @@ static bool is_parity(int kind) { return !(kind >= CL_ENV_LORENZ_RK4 && kind <= 
 // size that minimises ceil(blocks / SMs) * block (ties -> larger block).  65,536 envs on 148
 // SMs: 64-thread blocks give 7 x 64 = 448 threads on the fullest SM vs 512 for 128 / 256.
 static int pick_block(int64_t n, int sms) {
+  // ties -> the smaller block: at 1 Mi envs 64 / 128 / 256 are within 1 % of each other in balance and
+  // 64-thread blocks measured 1-5 % faster on every HBM-bound kind (profiles/r02_sweep_block_stats.jsonl)
   const int cand[3] = {64, 128, 256};
-  int64_t cost[3], best_cost = -1;
+  int best = 64;
+  int64_t best_cost = -1;
   for (int k = 0; k < 3; ++k) {
     const int64_t blocks = (n + cand[k] - 1) / cand[k];
-    cost[k] = ((blocks + sms - 1) / sms) * cand[k];
-    if (best_cost < 0 || cost[k] < best_cost) best_cost = cost[k];
+    const int64_t cost = ((blocks + sms - 1) / sms) * cand[k];
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cand[k]; }
   }
-  // the largest block within 1.5 % of the best balance: per-block work (the episode-statistics flush, the
-  // streamed mode's flag poll) is then shared by more envs -- at 1 Mi envs all three sizes are within 1 %
-  int best = 64;
-  for (int k = 0; k < 3; ++k)
-    if (cost[k] * 1000 <= best_cost * 1015) best = cand[k];
   return best;
 }
 

@@ -701,5 +701,6 @@ template <> struct StepMinBlocks<EnvPMSMClassic> { enum { value = 4 }; };
 template <> struct StepMinBlocks<EnvPMSMSingle> { enum { value = 4 }; };
 template <> struct StepMinBlocks<EnvMemristive4Pair> { enum { value = 4 }; };
 template <> struct StepMinBlocks<EnvPMSMFree> { enum { value = 5 }; };
+template <> struct StepBlockStats<EnvMemristive4Pair> { enum { value = 1 }; };
 
 }  // namespace cl

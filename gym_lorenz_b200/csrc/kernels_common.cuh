@@ -489,13 +489,21 @@ __device__ __forceinline__ void synth_action(const KParams& p, const Stream& rng
 // hr_sync 0.72 -> 0.76 of the copy bandwidth, pmsm_sync 0.61 -> 0.75, pmsm_classic 0.67 -> 0.68,
 // lorenz3 0.87 -> 0.88; 5 blocks cost lorenz3_pair / lorenz4_pair 2 % (spills), so they stay at 4.
 template <class E> struct StepMinBlocks { enum { value = 0 }; };
+// Kinds whose episodes end in a large share of the env-warps every step (memristive pair under full-range
+// forcing): k_step accumulates the episode statistics per block in shared memory and flushes once -- 65 -> 49 us
+// at 1 Mi envs.  Everywhere else the two block barriers and the flush cost 3-5 % of a 25-40 us step for
+// nothing (measured, profiles/r02_sweep_block_stats.jsonl), so it is a per-kind choice.
+template <class E> struct StepBlockStats { enum { value = 0 }; };
 
 template <class E, bool ROLL, bool PLAIN = false>
 __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_step(const KParams p) {
   extern __shared__ __align__(16) float sm_rows_all[];  // [warps per block][32 * OBS], row-store staging
-  __shared__ double s_stats[CL_NSTATS];                  // episode statistics of this block
-  if (threadIdx.x < CL_NSTATS) s_stats[threadIdx.x] = 0.0;
-  __syncthreads();
+  constexpr bool BLKSTATS = StepBlockStats<E>::value != 0;
+  __shared__ double s_stats[BLKSTATS ? CL_NSTATS : 1];   // episode statistics of this block
+  if (BLKSTATS) {
+    if (threadIdx.x < CL_NSTATS) s_stats[threadIdx.x] = 0.0;
+    __syncthreads();
+  }
   const int64_t i = p.i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < p.n;
   const unsigned lane = threadIdx.x & 31u;
@@ -586,7 +594,7 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
             a_next[c] = p.action[(int64_t)(t + 1) * p.act_ts + i * p.act_es + c * p.act_cs];
         }
       }
-      const unsigned dall = env_interval<E, ROLL, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin, &pend, s_stats);
+      const unsigned dall = env_interval<E, ROLL, PLAIN, SPEC>(s, ep_len, ep_ret, p, i, live, lane, t, step, a, want_noise, obs64, autoreset, bad_acc, sm_rows, fin, &pend, BLKSTATS ? s_stats : nullptr);
       if (!ROLL && !PLAIN && p.warp_done != nullptr && dall && lane == 0) p.warp_done[i >> 5] = 1;
     }
   };
@@ -597,14 +605,16 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
   } else {
     intervals(SpecTag<0>{});
   }
-  if (bad_acc && lane == 0) atomicAdd(&s_stats[CL_STAT_NONFINITE], (double)bad_acc);
+  if (bad_acc && lane == 0) atomicAdd(BLKSTATS ? &s_stats[CL_STAT_NONFINITE] : &p.stats[CL_STAT_NONFINITE], (double)bad_acc);
   if (live) {
     E::store(s, p, i);
     p.ep_len[i] = ep_len;
     p.ep_return[i] = ep_ret;
   }
-  __syncthreads();
-  if (threadIdx.x < CL_NSTATS && s_stats[threadIdx.x] != 0.0) atomicAdd(&p.stats[threadIdx.x], s_stats[threadIdx.x]);
+  if (BLKSTATS) {
+    __syncthreads();
+    if (threadIdx.x < CL_NSTATS && s_stats[threadIdx.x] != 0.0) atomicAdd(&p.stats[threadIdx.x], s_stats[threadIdx.x]);
+  }
 }
 
 // ---- the dynamic rollout kernel ---------------------------------------------------------
