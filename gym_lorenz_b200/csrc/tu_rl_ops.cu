@@ -254,19 +254,28 @@ __global__ void __launch_bounds__(256) k_frame_stack(float* __restrict__ stacked
 }
 
 // ---- evaluation metrics over stored trajectories err[T][3][stride], u[T][2][stride] (f64) ---
-// out[i][8] = mae, rmse, settling_time (NaN = never settles), energy, mae_c0..2 ... see header
-__global__ void __launch_bounds__(256) k_eval_metrics(const double* __restrict__ err, const double* __restrict__ u,
+// out[i][4] = mae, rmse, settling_time (NaN = never settles), energy -- see the header.
+// One thread per trajectory walking all T steps is latency-bound with a few thousand trajectories (ncu:
+// 85 % long-scoreboard, 382 GB/s; 746 GB/s with four steps of loads in flight).  The time axis is
+// therefore cut into segments (blockIdx.y): k_eval_partial accumulates per (trajectory, segment) and adds
+// its sums / last-exceedance indices into a scratch row with atomics, k_eval_final turns the row into the
+// four metrics.  Scratch row (f64): [0..3] sum|e_c|, [4..7] sum e_c^2, [8] energy, [9..12] last index with
+// |e_c| > band as a double (-1 = never; max-merged as an integer, see atomic_max_index).
+__device__ __forceinline__ void atomic_max_index(double* addr, int v) {
+  // indices are >= 0 and stored as v + 1 in a 64-bit integer view of the slot (0 = never exceeded)
+  atomicMax((unsigned long long*)addr, (unsigned long long)(v + 1));
+}
+
+__global__ void __launch_bounds__(128) k_eval_partial(const double* __restrict__ err, const double* __restrict__ u,
                                                       int T, int ncomp, int nctrl, int64_t n, int64_t stride,
-                                                      int steady_start, double dt, double band,
-                                                      double* __restrict__ out) {
+                                                      int steady_start, double band, int seg_len,
+                                                      double* __restrict__ scratch) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const int t_lo = (int)blockIdx.y * seg_len, t_hi = min(T, t_lo + seg_len);
   double sa[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, en = 0.0;
   int last_ex[4] = {-1, -1, -1, -1};
-  // One thread per trajectory walks T steps; with a few thousand trajectories there are too few threads to
-  // cover the memory latency one step at a time (ncu: 85 % long-scoreboard, 382 GB/s).  The loads of U
-  // consecutive steps are issued together, the sums then run in the reference's order (t ascending).
-  constexpr int U = 4;   // measured: 3.45 ms (1 step at a time) -> 1.76 ms (4) -> 2.0 ms (8) for 2000 x 16,384 trajectories
+  constexpr int U = 4;
   auto step = [&](int t, const double* e, const double* a) {
     for (int c = 0; c < ncomp; ++c) {
       if (fabs(e[c]) > band) last_ex[c] = t;
@@ -276,8 +285,8 @@ __global__ void __launch_bounds__(256) k_eval_metrics(const double* __restrict__
     for (int c = 0; c < nctrl; ++c) q += a[c] * a[c];
     en += q;
   };
-  int t = 0;
-  for (; t + U <= T; t += U) {
+  int t = t_lo;
+  for (; t + U <= t_hi; t += U) {
     double e[U][4], a[U][4];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(256) k_eval_metrics(const double* __restrict__
 #pragma unroll
     for (int k = 0; k < U; ++k) step(t + k, e[k], a[k]);
   }
-  for (; t < T; ++t) {
+  for (; t < t_hi; ++t) {
     double e[4], a[4];
     for (int c = 0; c < 4; ++c) {
       e[c] = c < ncomp ? err[((int64_t)t * ncomp + c) * stride + i] : 0.0;
@@ -298,21 +307,36 @@ __global__ void __launch_bounds__(256) k_eval_metrics(const double* __restrict__
     }
     step(t, e, a);
   }
+  double* row = scratch + i * 13;
+  for (int c = 0; c < ncomp; ++c) {
+    if (sa[c] != 0.0) atomicAdd(&row[c], sa[c]);
+    if (sq[c] != 0.0) atomicAdd(&row[4 + c], sq[c]);
+    if (last_ex[c] >= 0) atomic_max_index(&row[9 + c], last_ex[c]);
+  }
+  if (en != 0.0) atomicAdd(&row[8], en);
+}
+
+__global__ void __launch_bounds__(128) k_eval_final(const double* __restrict__ scratch, int T, int ncomp, int64_t n,
+                                                    int steady_start, double dt, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* row = scratch + i * 13;
   const double m = (double)(T - steady_start);
   double mae = 0.0, rmse = 0.0, ts = -1.0;
   bool never = false;
   for (int c = 0; c < ncomp; ++c) {
-    mae += sa[c] / m;
-    rmse += sqrt(sq[c] / m);
-    if (last_ex[c] + 1 >= T) never = true;                       // np.nan for that component
-    const double tc = (last_ex[c] < 0) ? 0.0 : (double)(last_ex[c] + 1) * dt;
-    if (last_ex[c] + 1 < T && tc > ts) ts = tc;                   // np.nanmax ignores the NaNs
+    mae += row[c] / m;
+    rmse += sqrt(row[4 + c] / m);
+    const int last_ex = (int)(*(const unsigned long long*)&row[9 + c]) - 1;
+    if (last_ex + 1 >= T) never = true;                       // np.nan for that component
+    const double tc = (last_ex < 0) ? 0.0 : (double)(last_ex + 1) * dt;
+    if (last_ex + 1 < T && tc > ts) ts = tc;                   // np.nanmax ignores the NaNs
   }
   double* o = out + i * 4;
   o[0] = mae / ncomp;
   o[1] = rmse / ncomp;
   o[2] = (ts < 0.0 && never) ? nan("") : (ts < 0.0 ? 0.0 : ts);
-  o[3] = en * dt;
+  o[3] = row[8] * dt;
 }
 
 int fail_if(cudaError_t e) { return e == cudaSuccess ? CL_OK : CL_ECUDA; }
@@ -443,7 +467,19 @@ extern "C" int cl_eval_metrics(void* stream, const double* err, const double* ct
       steady_start >= T)
     return CL_EINVAL;
   const int block = 128;
-  k_eval_metrics<<<(unsigned)((n + block - 1) / block), block, 0, (cudaStream_t)stream>>>(
-      err, ctrl, T, n_err, n_ctrl, n, stride, steady_start, dt, error_band, out4);
+  cudaStream_t st = (cudaStream_t)stream;
+  // enough (trajectory, segment) threads to cover the memory latency: ~512 K, segments of at least 64 steps
+  int64_t segs = (512 * 1024 + n - 1) / n;
+  if (segs > (T + 63) / 64) segs = (T + 63) / 64;
+  if (segs < 1) segs = 1;
+  const int seg_len = (int)((T + segs - 1) / segs);
+  segs = (T + seg_len - 1) / seg_len;
+  double* scratch = nullptr;
+  if (cudaMallocAsync((void**)&scratch, sizeof(double) * 13 * (size_t)n, st) != cudaSuccess) return CL_ENOMEM;
+  if (cudaMemsetAsync(scratch, 0, sizeof(double) * 13 * (size_t)n, st) != cudaSuccess) return CL_ECUDA;
+  const dim3 grid((unsigned)((n + block - 1) / block), (unsigned)segs);
+  k_eval_partial<<<grid, block, 0, st>>>(err, ctrl, T, n_err, n_ctrl, n, stride, steady_start, error_band, seg_len, scratch);
+  k_eval_final<<<grid.x, block, 0, st>>>(scratch, T, n_err, n, steady_start, dt, out4);
+  cudaFreeAsync(scratch, st);
   return fail_if(cudaGetLastError());
 }
