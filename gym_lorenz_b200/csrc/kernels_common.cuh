@@ -51,7 +51,6 @@ struct KParams {
   int32_t host_rows;
   const uint32_t* act_ready;
   uint32_t act_gen;
-  int32_t act_poll;        // unused (kept for ABI stability of the struct within this round)
   int32_t act_slice_envs;
   uint32_t* host_err;
   // rollout

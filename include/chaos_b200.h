@@ -280,7 +280,8 @@ int cl_measure_fma_peak(int32_t device, int32_t dtype_bytes, double seconds, dou
 int64_t cl_launch_count(const cl_ctx* ctx);
 /* threads per block the context chose for its env kernels (wave-quantisation aware) */
 int cl_block_size(const cl_ctx* ctx);
-/* cl_rollout calls served by the dynamically scheduled kernel (env-warp x interval-chunk tasks) */
+/* cl_rollout calls served by a dynamically scheduled kernel (k_rollout_sm or k_rollout_dyn: env-warp x
+ * interval-chunk tasks) instead of the static one-thread-per-env mapping */
 int64_t cl_dyn_launch_count(const cl_ctx* ctx);
 /* rollouts that ran on the plain-I/O instantiation of the rollout kernels (FP64-bound kinds:
  * float32 SoA observation planes, real-typed reward, done flags, auto-reset, no term_obs) */
