@@ -500,6 +500,8 @@ extern "C" int cl_rollout(cl_ctx* ctx, void* stream, const cl_buffers* buf, cons
           if (sc > d->T) sc = d->T;
           if (cmax <= 64) {
             p.sm_grid = grid; p.sm_workers = workers; p.sm_chunk = sc;
+            p.sm_gdiv = 1;
+            if (const char* w = getenv("CHAOS_B200_SM_GDIV")) { const int k = atoi(w); if (k >= 1 && k <= 16) p.sm_gdiv = k; }
             p.host_tmap = &tmap;
             p.sm_tmap_ok = action_tensor_map(&tmap, io->action, (uint64_t)W * 32, (uint64_t)ctx->lay.act_dim,
                                              (uint64_t)d->T, (uint64_t)io->act_cs, (uint64_t)d->act_ts, (uint32_t)sc) ? 1 : 0;

@@ -77,7 +77,7 @@ struct KParams {
   uint32_t* dyn_progress;
   int32_t dyn_chunk, dyn_nchunks, dyn_nwarps, dyn_tma, dyn_grid;
   // SM-local rollout scheduling (k_rollout_sm): grid, worker warps per block, control intervals per task
-  int32_t sm_grid, sm_workers, sm_chunk;
+  int32_t sm_grid, sm_workers, sm_chunk, sm_gdiv;   // sm_gdiv: guest chunk = sm_chunk / sm_gdiv
   int32_t sm_tmap_ok;                  // *host_tmap describes the action tensor (x env, y channel, z interval)
   const CUtensorMap* host_tmap;        // host-side only: passed to k_rollout_sm as its own __grid_constant__ parameter
   // observations go out as contiguous, 16-byte aligned float32 rows -> warp-transposed vector stores
@@ -895,10 +895,13 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   // then chunks of Tc: chunk boundaries (action-buffer swaps, guest slots) of the warps sharing a
   // scheduler do not coincide, and the guests' last chunks have mixed lengths.  Every env-warp has the
   // same number of chunks; trailing chunks past T are empty.
-  const int Tc = p.sm_chunk;
-  const int nchunks = 1 + (p.T - 1 + Tc - 1) / Tc;
-  auto chunk_t0 = [&](int f, int c) { return c == 0 ? 0 : min(p.T, f + (c - 1) * Tc); };
-  auto chunk_len = [&](int f, int c) { return min(c == 0 ? f : Tc, p.T - chunk_t0(f, c)); };
+  // Guests use chunks of Tg = Tc / sm_gdiv intervals: every guest chunk a worker takes or does not take is
+  // that worker's imbalance at the end of the launch (all workers wait for the last one at the final barrier).
+  const int Tc = p.sm_chunk, Tg = max(1, Tc / max(1, p.sm_gdiv));
+  const int nchunks = 1 + (p.T - 1 + Tc - 1) / Tc;          // residents
+  const int nchunks_g = 1 + (p.T - 1 + Tg - 1) / Tg;        // guests
+  auto chunk_t0 = [&](int f, int c, int tc) { return c == 0 ? 0 : min(p.T, f + (c - 1) * tc); };
+  auto chunk_len = [&](int f, int c, int tc) { return min(c == 0 ? f : tc, p.T - chunk_t0(f, c, tc)); };
   const SmLayout<E> L(cmax, Tc);
   float* const act = (float*)(sm_raw + L.act);
   real* const st = (real*)(sm_raw + L.state);
@@ -924,8 +927,8 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   __syncthreads();
 
   // stage the actions of chunk c of local env-warp le into its buffer (c & 1)
-  auto stage = [&](int le, int f, int c) {
-    const int t0 = chunk_t0(f, c);
+  auto stage = [&](int le, int f, int c, int tc) {
+    const int t0 = chunk_t0(f, c, tc);
     uint64_t* bar = &mbar[le * 3 + (c & 1)];
     float* dst = act + (size_t)(le * 2 + (c & 1)) * per_buf;
     if (p.sm_tmap_ok) {
@@ -936,7 +939,7 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
         tma_load_3d(dst, &tmap, (e0 + le) * 32, 0, t0, bar);
       }
     } else {
-      const int len = chunk_len(f, c);
+      const int len = chunk_len(f, c, tc);
       if (lane == 0) mbar_expect_tx(bar, (uint32_t)(len * E::ACT * 128));
       __syncwarp();
       for (int k = (int)lane; k < len * E::ACT; k += 32) {  // every expected byte must be issued
@@ -952,7 +955,7 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) spin_guard(spins);
   };
-  for (int le = wib; le < cnt; le += nres) stage(le, 1 + le * Tc / cnt, 0);
+  for (int le = wib; le < cnt; le += nres) { const int tc = le < nres ? Tc : Tg; stage(le, 1 + le * tc / cnt, 0, tc); }
 
   const uint64_t step0 = step_base(p);
   unsigned bad_acc = 0u;
@@ -981,7 +984,8 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   // ---- worker loop: own chunks in order, a guest chunk whenever the Bresenham credit says so.
   // ONE call site of run_chunk (the unrolled interval body is ~13 KB of code per specialisation; a second
   // inlined copy would double the instruction-cache footprint of the hot loop).
-  const uint32_t g_total = (uint32_t)ng * (uint32_t)nchunks;
+  const uint32_t g_total = (uint32_t)ng * (uint32_t)nchunks_g;
+  const int g_credit = ng * (Tc / Tg);     // guest chunks owed per round of own chunks, times nres
   typename E::S s = {};
   int32_t ep_len = 0;
   double ep_ret = 0.0;
@@ -990,7 +994,7 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
   pend.valid = 0u;
   int in_regs = -1;                     // local env-warp whose state is in this warp's registers
   int c_own = 0;
-  int credit = (wib * ng) % nres;       // phase shift: the workers' guest slots interleave evenly in time
+  int credit = (wib * g_credit) % nres; // phase shift: the workers' guest slots interleave evenly in time
   bool guests_left = ng > 0, want_guest = false;
   for (;;) {
     int le, c;
@@ -1009,8 +1013,9 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
     } else {
       break;
     }
-    const int f = 1 + le * Tc / cnt;
-    const int t0 = chunk_t0(f, c), len = chunk_len(f, c);
+    const int tc = guest ? Tg : Tc, nch = guest ? nchunks_g : nchunks;
+    const int f = 1 + le * tc / cnt;
+    const int t0 = chunk_t0(f, c, tc), len = chunk_len(f, c, tc);
     const int64_t i = (int64_t)(e0 + le) * 32 + lane;
     const bool live = i < p.n;
     if (guest && c > 0) {
@@ -1036,7 +1041,7 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
     // before.  No fence.proxy.async here -- it compiles to MEMBAR.ALL.CTA, which also waits for this
     // warp's outstanding global output stores; the write-after-read direction is ordered by the mbarrier
     // alone (the usual TMA pipeline pattern).
-    if (c + 1 < nchunks) stage(le, f, c + 1);
+    if (c + 1 < nch) stage(le, f, c + 1, tc);
     if (in_regs != le) {
       E::load_sm(s, st + (size_t)le * E::NSTATE * 32, lane);
       ep_len = s_len[le * 32 + lane];
@@ -1054,7 +1059,7 @@ __global__ void __launch_bounds__(CL_SM_THREADS, CL_SM_MINB) k_rollout_sm(const 
       want_guest = false;               // one guest chunk per slot
     } else {
       c_own += 1;
-      credit += ng;
+      credit += g_credit;
       want_guest = guests_left && credit >= nres && c_own < nchunks;
       if (want_guest) credit -= nres;
       park = want_guest || c_own == nchunks;

@@ -255,6 +255,29 @@ def test_sm_local_rollout_is_bit_identical_to_static(kind, n, T, workers, chunk,
         assert np.isclose(s0["return_sum"], s1["return_sum"], rtol=1e-9)
 
 
+@pytest.mark.parametrize("gdiv", ["2", "4", "16"])
+def test_sm_local_rollout_guest_chunk_divisor(gdiv, monkeypatch):
+    """Guests may use shorter chunks than residents (CHAOS_B200_SM_GDIV): same bits as the static kernel."""
+    import torch
+    n, T = 65536, 53
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CHAOS_B200_DYN", mode)
+        monkeypatch.setenv("CHAOS_B200_SM_GDIV", gdiv)
+        b = H.gpu_batch("lorenz_rk4", n, seed=17, autoreset=True, max_episode_steps=13)
+        b.reset()
+        g = torch.Generator(device="cpu").manual_seed(8)
+        soa = (torch.rand((T, b.act_dim, b.n_pad), generator=g) * 2 - 1).to(b.device)
+        out = b.rollout(T, soa[:, :, :n].permute(0, 2, 1))
+        torch.cuda.synchronize()
+        assert b.sm_launch_count == (1 if mode == "1" else 0)
+        res[mode] = (out["obs"].clone(), out["reward"].clone(), out["done"].clone(), b.state.clone(), b.ep_len.clone(),
+                     b.ep_return.clone())
+        b.close()
+    for x, y in zip(res["0"], res["1"]):
+        assert torch.equal(x, y)
+
+
 def test_sm_local_rollout_repeated_launches_and_jitter(monkeypatch):
     """Back-to-back launches (state leaves and re-enters shared memory every launch) with per-env
     parameters (the generic, register-parameter interval loop) against the static kernel."""
