@@ -1,11 +1,15 @@
 """TEST INFRASTRUCTURE ONLY -- NumPy restatements of the stable_baselines3==2.7.1 pieces that the
 reference's pipelines wrap around the env (the library is un-vendored and not installed here:
-"parity unpinned" by any reference artefact; these follow SB3's published source) and of the
-reference's own metric functions.
+these follow SB3's published source) and of the reference's own metric functions.  What the
+reference's own SB3 artefacts hold about these pieces (the pickled VecNormalize objects and model zips of
+code/lorenz_pmsm/train.py's eight finished runs: update schedule and counts of obs_rms / ret_rms, defaults,
+Monitor records, TimeLimit) is extracted by tests/golden/make_sb3_artefact_golden.py and checked in
+tests/test_sb3_artefacts.py; the moment-merge arithmetic and GAE are pinned by no artefact.
 
   gae                       common/buffers.py::RolloutBuffer.compute_returns_and_advantage
   RunningMeanStd            common/running_mean_std.py
   normalize_obs             common/vec_env/vec_normalize.py::_normalize_obs / normalize_obs
+  VecNormalizeRef           common/vec_env/vec_normalize.py::VecNormalize.reset / step_wait / _update_reward
   frame_stack_update        common/vec_env/stacked_observations.py::StackedObservations.update (1-D obs)
   calculate_advanced_metrics, steady_state_metrics
                             /root/reference/code/lorenz_pmsm/test_evaluate.py:25-59, :239-250
@@ -55,6 +59,51 @@ class RunningMeanStd:
 
 def normalize_obs(obs, rms, clip_obs=10.0, epsilon=1e-8):
     return np.clip((obs - rms.mean) / np.sqrt(rms.var + epsilon), -clip_obs, clip_obs).astype(np.float32)
+
+
+class VecNormalizeRef:
+    """VecNormalize over a callable env pair: `reset_fn() -> obs [N, D]`, `step_fn(actions) -> (obs, rewards,
+    dones)` (auto-resetting, like DummyVecEnv).  Statement order of SB3's reset() / step_wait()."""
+
+    def __init__(self, reset_fn, step_fn, num_envs, obs_dim, training=True, norm_obs=True, norm_reward=True,
+                 clip_obs=10.0, clip_reward=10.0, gamma=0.99, epsilon=1e-8):
+        self.reset_fn, self.step_fn = reset_fn, step_fn
+        self.training, self.norm_obs, self.norm_reward = training, norm_obs, norm_reward
+        self.clip_obs, self.clip_reward, self.gamma, self.epsilon = clip_obs, clip_reward, gamma, epsilon
+        self.obs_rms = RunningMeanStd(shape=(obs_dim,))
+        self.ret_rms = RunningMeanStd(shape=())
+        self.returns = np.zeros(num_envs)
+        self.old_obs = self.old_reward = None
+
+    def normalize_obs(self, obs):
+        return normalize_obs(obs, self.obs_rms, self.clip_obs, self.epsilon) if self.norm_obs else obs
+
+    def normalize_reward(self, reward):
+        if not self.norm_reward:
+            return reward
+        return np.clip(reward / np.sqrt(self.ret_rms.var + self.epsilon), -self.clip_reward,
+                       self.clip_reward).astype(np.float32)
+
+    def reset(self):
+        obs = self.reset_fn()
+        self.old_obs = obs
+        self.returns = np.zeros(len(self.returns))
+        if self.training and self.norm_obs:
+            self.obs_rms.update(obs)
+        return self.normalize_obs(obs)
+
+    def step(self, actions):
+        obs, rewards, dones = self.step_fn(actions)
+        self.old_obs, self.old_reward = obs, rewards
+        if self.training and self.norm_obs:
+            self.obs_rms.update(obs)
+        nobs = self.normalize_obs(obs)
+        if self.training:                                   # _update_reward: not gated on norm_reward
+            self.returns = self.returns * self.gamma + rewards
+            self.ret_rms.update(self.returns)
+        nrew = self.normalize_reward(rewards)
+        self.returns[np.asarray(dones, bool)] = 0
+        return nobs, nrew, dones
 
 
 def frame_stack_update(stacked, obs, dones):
