@@ -79,13 +79,13 @@ struct HostStage {
   cudaEvent_t ev_fork, ev_join;
   // CL_HOST_STREAMED: the step kernel is launched first and waits, block by block, for the slice of
   // the pinned action buffer it reads to be published (generation number) by the staging loop
-  uint32_t* h_ready;   // pinned word: (generation << 8) | slices staged so far
-  uint32_t* d_ready;   // its device mirror, kept up to date by k_relay
+  uint32_t* h_ready;   // pinned progress words, one per staging lane (CL_STAGE_WORD_STRIDE apart): (generation << 8) | slices of the lane staged so far
+  uint32_t* d_ready;   // their device mirrors (adjacent words), kept up to date by k_relay
   uint32_t* h_err;     // pinned: set by a block whose bounded wait expired
   uint32_t gen;
   uint8_t* d_warp_done;  // device copy for CL_HOST_DMA (travels with the result block)
   size_t wd_bytes;
-  struct CopyHelper* helper;   // second staging thread (nullptr: single-threaded staging)
+  struct CopyHelper* helper;   // helper threads of the staging lanes (nullptr: single-threaded staging)
   cl_buffers redo_buf;         // buffers of the step in flight
   int64_t streamed_fallbacks;  // streamed steps called off by k_relay and redone as zero-copy steps
 };
@@ -304,34 +304,50 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
 
 __global__ void k_advance_step(uint64_t* step, uint64_t count) { *step += count; }
 
-// Streamed host mode.  Mirrors the pinned "slices staged" word ((gen << 8) | count) into device memory
-// until all `nslices` are published.  It is also the judge of whether streaming works at all: if NOTHING is
-// published within 20 ms of its start, the CPU is evidently not running concurrently with the GPU work
-// (a profiler or CUDA_LAUNCH_BLOCKING made the launches synchronous, so the staging loop only starts after
-// the kernels have finished).  It then writes count 255 = "called off": every block of the step kernel
-// exits before storing anything, *host_err = 2 tells cl_step_host_wait to redo the step from the (by then
-// complete) staging buffer without streaming and to keep this context out of streamed mode.
+// Streamed host mode.  Mirrors the pinned progress words of the staging lanes ((gen << 8) | slices of that lane
+// staged so far; host_copy.h) into device memory until every lane is complete: relay thread k reads lane k's
+// word (the system-scope reads of the lanes are in flight together) and is the only writer of its device
+// copy.  The warp is also the judge of whether streaming works at all: if NO lane has published anything
+// within 20 ms of its start, the CPU is evidently not running concurrently with the GPU work (a profiler or
+// CUDA_LAUNCH_BLOCKING made the launches synchronous, so the staging loop only starts after the kernels have
+// finished).  It then writes count 255 = "called off" to every lane: every block of the step kernel exits
+// before storing anything (no block can have passed its wait: nothing was mirrored), *host_err = 2 tells
+// cl_step_host_wait to redo the step from the (by then complete) staging buffer without streaming and to
+// keep this context out of streamed mode.  The decision is a warp vote taken in the same loop iteration by
+// all lanes, so "called off" and "a lane was mirrored" exclude each other.
 // *host_err = 1: published partially and then nothing for 2 s -- unrecoverable, reported as an error.
-__global__ void k_relay(const uint32_t* host_word, uint32_t* dev_word, uint32_t gen, uint32_t nslices, uint32_t* host_err) {
-  if (threadIdx.x != 0) return;
+__global__ void k_relay(const uint32_t* host_words, uint32_t* dev_words, uint32_t gen, uint32_t lanes, uint32_t spl,
+                        uint32_t nslices, uint32_t* host_err) {
+  const uint32_t k = threadIdx.x;
+  if (k >= lanes) return;
+  const unsigned mask = lanes >= 32u ? 0xffffffffu : ((1u << lanes) - 1u);
+  const uint32_t first = k * spl;
+  const uint32_t want = first >= nslices ? 0u : (nslices - first < spl ? nslices - first : spl);
+  const uint32_t* host_word = host_words + (size_t)k * CL_STAGE_WORD_STRIDE;
   uint32_t last = 0, polls = 0;
   uint64_t t0 = 0, t1 = 0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (;;) {
-    const uint32_t v = cl::ld_acquire_sys_u32(host_word);     // one system-scope read per ~4 us: the only one on the GPU
-    if ((v >> 8) == gen && (v & 255u) > last) {
-      last = v & 255u;
-      *(volatile uint32_t*)dev_word = v;
-      __threadfence();
-      if (last >= nslices) return;
+    if (last < want) {
+      const uint32_t v = cl::ld_acquire_sys_u32(host_word);   // one system-scope read per lane per ~4 us: the only ones on the GPU
+      if ((v >> 8) == gen && (v & 255u) > last && (v & 255u) <= want) {
+        last = v & 255u;
+        *(volatile uint32_t*)(dev_words + k) = v;
+        __threadfence();
+      }
     }
+    if (__all_sync(mask, last >= want)) return;
     if ((++polls & 7u) == 0u) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      const uint64_t waited = t1 - t0;
-      if ((last == 0 && waited > 20000000ull) || waited > 2000000000ull) {
-        *(volatile uint32_t*)dev_word = (gen << 8) | 255u;
-        __threadfence();
-        *host_err = last == 0 ? 2u : 1u;
+      const uint64_t waited = __shfl_sync(mask, t1 - t0, 0);
+      const bool none = !__any_sync(mask, last > 0u);
+      if ((none && waited > 20000000ull) || waited > 2000000000ull) {
+        if (last < want) {
+          *(volatile uint32_t*)(dev_words + k) = (gen << 8) | 255u;
+          __threadfence();
+        }
+        __syncwarp(mask);
+        if (k == 0) *host_err = none ? 2u : 1u;
         return;
       }
     }
@@ -616,8 +632,8 @@ static int host_stage_init(cl_ctx* ctx) {
   memset(h.h_ready, 0, 80 * sizeof(uint32_t));
   h.h_err = h.h_ready + 72;
   h.gen = 0;
-  CU(cudaMalloc((void**)&h.d_ready, sizeof(uint32_t)));
-  CU(cudaMemset(h.d_ready, 0, sizeof(uint32_t)));
+  CU(cudaMalloc((void**)&h.d_ready, CL_STAGE_MAX_LANES * sizeof(uint32_t)));
+  CU(cudaMemset(h.d_ready, 0, CL_STAGE_MAX_LANES * sizeof(uint32_t)));
   h.d_obs = (float*)h.d_out;
   h.d_rew = (float*)(h.d_out + N * O * sizeof(float));
   h.d_done = (uint8_t*)(h.d_out + N * O * sizeof(float) + N * sizeof(float));
@@ -723,9 +739,9 @@ static int host_step_launch(cl_ctx* ctx, cudaStream_t st, const cl_buffers* buf,
   if (mode == CL_HOST_STREAMED) {
     // 1. launch k_relay (side stream: mirrors the pinned "slices staged" word into device memory) and
     //    the step kernel, whose blocks wait for the slice they read;
-    // 2. stage the caller's array slice by slice into the pinned buffer, publishing the count after
-    //    each slice.  The final count is stored whatever happens in between, so both kernels always
-    //    terminate (and their waits are bounded anyway).
+    // 2. stage the caller's array into the pinned buffer: the slices are dealt out to staging lanes (one copy
+    //    thread each, host_copy.h), every lane publishes its count after each slice.  The final counts are
+    //    stored whatever happens in between, so both kernels always terminate (and their waits are bounded anyway).
     const int blk = ctx->block;
     int slices = h.slices < 1 ? 1 : (h.slices > 64 ? 64 : h.slices);
     size_t per = ((N + (size_t)slices - 1) / (size_t)slices + (size_t)blk - 1) / (size_t)blk * (size_t)blk;   // whole blocks
@@ -733,19 +749,27 @@ static int host_step_launch(cl_ctx* ctx, cudaStream_t st, const cl_buffers* buf,
     if (h.gen == 0) h.gen = 1;
     *h.h_err = 0u;
     const uint32_t nsl = (uint32_t)((N + per - 1) / per);
-    __atomic_store_n(&h.h_ready[0], h.gen << 8, __ATOMIC_RELEASE);
-    p.act_ready = h.d_ready; p.act_gen = h.gen; p.act_slice_envs = (int32_t)per; p.host_err = h.h_err;
-    k_relay<<<1, 32, 0, h.side>>>(h.h_ready, h.d_ready, h.gen, nsl, h.h_err);
+    uint32_t spl = 1;
+    const uint32_t lanes = stage_plan(h.helper, nsl, &spl);
+    for (uint32_t k = 0; k < lanes; ++k)
+      __atomic_store_n(&h.h_ready[k * CL_STAGE_WORD_STRIDE], h.gen << 8, __ATOMIC_RELEASE);
+    // whatever happens below, the relay (and any block already running) must get to see every lane complete
+    auto publish_all = [&]() {
+      for (uint32_t k = 0; k < lanes; ++k)
+        __atomic_store_n(&h.h_ready[k * CL_STAGE_WORD_STRIDE], (h.gen << 8) | stage_lane_count(k, spl, nsl), __ATOMIC_RELEASE);
+    };
+    p.act_ready = h.d_ready; p.act_gen = h.gen; p.act_slice_envs = (int32_t)per; p.act_lane_slices = (int32_t)spl;
+    p.host_err = h.h_err;
+    k_relay<<<1, 32, 0, h.side>>>(h.h_ready, h.d_ready, h.gen, lanes, spl, nsl, h.h_err);
     if (cudaGetLastError() != cudaSuccess) {
-      __atomic_store_n(&h.h_ready[0], (h.gen << 8) | nsl, __ATOMIC_RELEASE);
+      publish_all();
       return fail(ctx, CL_ECUDA, "relay kernel launch failed");
     }
     r = launch(ctx, p, cl::MODE_STEP, st);
     if (r == CL_OK)
       stage_slices(h.helper, (unsigned char*)h.h_act, (const unsigned char*)action_host, per * A * sizeof(float),
                    N * A * sizeof(float), nsl, h.gen, h.h_ready);
-    // whatever happened, the relay (and any block already running) must see the final count
-    __atomic_store_n(&h.h_ready[0], (h.gen << 8) | nsl, __ATOMIC_RELEASE);
+    publish_all();
     if (r) return r;
   } else if (mode == CL_HOST_PIPELINED && h.slices > 1) {
     // slice j runs on stream (j & 1): [DMA its actions in] -> [kernel: step, write results to host].

@@ -52,6 +52,7 @@ struct KParams {
   const uint32_t* act_ready;
   uint32_t act_gen;
   int32_t act_slice_envs;
+  int32_t act_lane_slices;   // slices per staging lane; lane k's progress word is act_ready[k]
   uint32_t* host_err;
   // rollout
   int32_t T;
@@ -148,7 +149,8 @@ __device__ __forceinline__ uint64_t step_base(const KParams& p) {
 __global__ void k_advance_step(uint64_t* step, uint64_t count);
 // Streamed host mode: mirrors the pinned "slices staged" word (gen << 8 | count) into device memory until
 // all `nslices` of generation `gen` are published (bounded: ~2 s).
-__global__ void k_relay(const uint32_t* host_word, uint32_t* dev_word, uint32_t gen, uint32_t nslices, uint32_t* host_err);
+__global__ void k_relay(const uint32_t* host_words, uint32_t* dev_words, uint32_t gen, uint32_t lanes, uint32_t spl,
+                        uint32_t nslices, uint32_t* host_err);
 
 // n uniforms in [lo,hi) (NumPy construction), 2 per Philox block.
 template <int N>
@@ -524,9 +526,10 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
   const bool streamed = !ROLL && p.act_ready != nullptr;   // block-uniform
   if (streamed) {
     // Streamed host mode: this kernel was launched BEFORE the CPU finished staging the caller's action
-    // array into the pinned buffer.  The CPU publishes the number of slices staged so far (act_slice_envs
-    // envs each, a whole number of blocks) in a pinned word; k_relay (one thread, side stream) mirrors
-    // that word into device memory, and every block polls the DEVICE copy: uncached reads of host memory
+    // array into the pinned buffer.  The slices (act_slice_envs envs each, a whole number of blocks) are dealt
+    // out to staging lanes of act_lane_slices slices, one CPU thread each; every lane publishes the number of
+    // its slices staged so far in a pinned word of its own; k_relay (one warp, side stream) mirrors those
+    // words into device memory, and every block polls the DEVICE copy of its lane: uncached reads of host memory
     // cost ~4 us each and are served one at a time (measured: 1 ms per step when all 256 blocks polled
     // the host word themselves), a device word is an L2 hit.  The state loads above are already in
     // flight meanwhile.  If the relay reports that the CPU is not publishing at all (launches made
@@ -534,8 +537,10 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
     // block leaves before it has stored anything and cl_step_host_wait redoes the step without streaming.
     __shared__ int s_abort;
     if (threadIdx.x == 0) {
-      const uint32_t need = (uint32_t)((i - p.i_begin) / p.act_slice_envs) + 1u;
-      const volatile uint32_t* word = p.act_ready;
+      const uint32_t slice = (uint32_t)((i - p.i_begin) / p.act_slice_envs);
+      const uint32_t spl = p.act_lane_slices > 0 ? (uint32_t)p.act_lane_slices : 0xffffffffu;
+      const uint32_t need = slice % spl + 1u;
+      const volatile uint32_t* word = p.act_ready + slice / spl;
       uint64_t t0 = 0, t1 = 0;
       uint32_t polls = 0;
       int ab = 0;

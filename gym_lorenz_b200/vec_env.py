@@ -233,8 +233,8 @@ class BatchedChaosVecEnv(VecEnv):
     def __init__(self, kind: str = "hr_sync", num_envs: int = 1, *, device="cuda:0", seed: int = 0,
                  monitor: bool = True, copy_outputs: Optional[bool] = None, **kwargs):
         """`copy_outputs`: SB3's DummyVecEnv returns fresh copies of obs / rewards / dones every step.
-        True does the same; False returns zero-copy views of a ring of 3 pinned result slots, valid
-        until the third following step (enough for SB3's own algorithms, which copy what they keep
+        True does the same; False returns zero-copy views of a ring of 3 pinned result slots (obs, rewards,
+        and `dones` on steps in which no episode ended), valid until the third following step (enough for SB3's own algorithms, which copy what they keep
         at once); None (default) copies while obs + reward are at most 256 KiB per step and aliases
         above.  `infos` is one list object reused across steps either way: entries of envs that
         finished an episode are rebuilt each step, so keep `infos[i]` dicts, not the list."""
@@ -270,9 +270,14 @@ class BatchedChaosVecEnv(VecEnv):
         obs, rew, done, term_obs, ler, lel, n_done = self.batch.step_host_wait()
         self._waiting = False
         infos = self._infos
-        dones = done != 0
         pending = None
-        if n_done:
+        if not n_done:
+            # nobody finished: every flag byte is 0, i.e. already a valid all-False bool array.  Without
+            # copies that view IS the result (like obs / rewards it lives in the 3-slot ring); comparing
+            # 65,536 bytes would cost 5 us of an 80 us step
+            dones = done.view(np.bool_) if not self._copy_outputs else np.zeros(self.num_envs, np.bool_)
+        else:
+            dones = done != 0
             idx = np.flatnonzero(dones)
             flags = done[idx]
             trunc = (((flags & L.DONE_TRUNCATED) != 0) & ((flags & L.DONE_TERMINATED) == 0)).tolist()

@@ -1,6 +1,8 @@
 """The SB3 VecEnv contract (stable_baselines3 2.7.1 DummyVecEnv semantics) on the GPU env,
 plus the single-env facades, attribute access used by the reference's scripts, DLPack
 hand-off and checkpoint/resume."""
+import os
+
 import numpy as np
 import pytest
 
@@ -65,7 +67,8 @@ def test_step_wait_output_lifetime():
     for k in (1, 2):
         env.step(act())
         assert np.array_equal(obs_t, snap_o) and np.array_equal(rew_t, snap_r), f"overwritten after {k} more steps"
-    obs_3, _, _, _ = env.step(act())
+    obs_3, _, d_3, _ = env.step(act())
+    assert d_3.dtype == np.bool_ and d_3.shape == (n,) and not d_3.any()   # nobody finished: all-False view of the slot
     assert np.shares_memory(obs_3, obs_t)                      # the ring wrapped around ...
     assert not np.array_equal(obs_t, snap_o)                   # ... so the old view now shows step t+3
     env.close()
@@ -279,12 +282,19 @@ def test_host_step_modes_give_identical_results(kind):
     from gym_lorenz_b200.vec_env import BatchedChaosVecEnv
     n, T = 20000 + 37, 9
     modes = [("dma", 1), ("zerocopy", 1), ("pipelined", 2), ("pipelined", 3), ("pipelined", 7), ("pipelined", 64),
-             ("streamed", 1), ("streamed", 3), ("streamed", 16), ("streamed", 64)]
+             ("streamed", 1), ("streamed", 3), ("streamed", 16), ("streamed", 64),
+             # staging lanes (copy threads): 1 .. 4, slice counts that do and do not divide by the lanes
+             ("streamed", 16, 1), ("streamed", 5, 2), ("streamed", 16, 3), ("streamed", 2, 4), ("streamed", 37, 4)]
     rng = np.random.default_rng(5)
     ref = None
-    for mode, k in modes:
+    for mode, k, *threads in modes:
+        if threads:
+            os.environ["CHAOS_B200_COPY_THREADS"] = str(threads[0])
+        else:
+            os.environ.pop("CHAOS_B200_COPY_THREADS", None)
         env = BatchedChaosVecEnv(kind, n, seed=3, max_episode_steps=4)
-        env.batch.set_host_mode(mode, k)
+        env.batch.set_host_mode(mode, k)        # creates the staging context (reads the variable)
+        os.environ.pop("CHAOS_B200_COPY_THREADS", None)
         a_rng = np.random.default_rng(11)
         lo, hi = env.action_space.low, env.action_space.high
         trace = [env.reset().copy()]

@@ -1,8 +1,9 @@
 """CPU stress test of the streamed host mode's staging protocol (csrc/host_copy.h, plain C++): the
-stepping thread and the helper thread copy alternate slices of a caller-owned array into the staging
-buffer and advance the published "slices staged" word monotonically; a checker thread playing the GPU
-side verifies, every time it sees the word move, that all slices below the published count already
-hold the new data (release/acquire + store fence after the streaming stores)."""
+slices of a caller-owned array are dealt out to up to four staging lanes (stepping thread + helper threads),
+each lane copies its contiguous range slice by slice and advances its own published "slices staged" word
+monotonically; a checker thread playing the GPU side verifies, every time it sees a lane's word move, that
+all slices of that lane below the published count already hold the new data (release/acquire + store fence
+after the streaming stores)."""
 import os
 import shutil
 import subprocess
@@ -24,30 +25,33 @@ HARNESS = textwrap.dedent(r'''
       const size_t total = 786432 + 12 * 37;          // not a multiple of the slice size
       unsigned char* dst = (unsigned char*)aligned_alloc(4096, (total + 4095) / 4096 * 4096);
       std::vector<std::vector<unsigned char>> srcs(4, std::vector<unsigned char>(total));
-      uint32_t* word = (uint32_t*)aligned_alloc(64, 64);
-      *word = 0;
-      CopyHelper* helper = nullptr;
-      if (threads >= 2) {
-        helper = (CopyHelper*)calloc(1, sizeof(CopyHelper));
-        if (pthread_create(&helper->th, nullptr, copy_helper_main, helper) != 0) return 2;
-        helper->started = true;
-      }
-      std::atomic<uint32_t> cur_gen{0}, cur_nsl{0}, errors{0}, stop{0};
+      const int W = CL_STAGE_MAX_LANES * CL_STAGE_WORD_STRIDE;
+      uint32_t* words = (uint32_t*)aligned_alloc(64, W * sizeof(uint32_t));
+      for (int k = 0; k < W; ++k) words[k] = 0;
+      CopyHelper* helper = copy_helper_start_n(threads);
+      if (threads >= 2 && (!helper || helper->n_workers != threads - 1)) return 2;
+      std::atomic<uint32_t> cur_gen{0}, cur_nsl{0}, cur_spl{1}, errors{0}, stop{0};
       std::atomic<size_t> cur_per{0};
       std::atomic<int> cur_src{0};
-      std::thread checker([&] {
-        uint32_t last_word = 0;
+      std::thread checker([&] {          // plays the GPU side: every lane's word on its own
+        uint32_t last_word[CL_STAGE_MAX_LANES] = {0, 0, 0, 0};
         while (!stop.load()) {
-          const uint32_t w = __atomic_load_n(word, __ATOMIC_ACQUIRE);
-          if (w == last_word) continue;
-          if ((w >> 8) == (last_word >> 8) && (w & 255u) < (last_word & 255u)) errors++;   // went backwards
-          last_word = w;
-          const uint32_t gen = w >> 8, cnt = w & 255u;
-          if (gen != cur_gen.load() || cnt == 0) continue;
-          const size_t per = cur_per.load();
-          const unsigned char* s = srcs[cur_src.load()].data();
-          const size_t upto = (size_t)cnt * per < total ? (size_t)cnt * per : total;
-          if (gen == cur_gen.load() && memcmp(dst, s, upto) != 0 && gen == cur_gen.load()) errors++;
+          for (int lane = 0; lane < CL_STAGE_MAX_LANES; ++lane) {
+            const uint32_t w = __atomic_load_n(words + lane * CL_STAGE_WORD_STRIDE, __ATOMIC_ACQUIRE);
+            if (w == last_word[lane]) continue;
+            if ((w >> 8) == (last_word[lane] >> 8) && (w & 255u) < (last_word[lane] & 255u)) errors++;   // went backwards
+            last_word[lane] = w;
+            const uint32_t gen = w >> 8, cnt = w & 255u;
+            if (gen != cur_gen.load() || cnt == 0) continue;
+            const size_t per = cur_per.load();
+            const uint32_t spl = cur_spl.load();
+            const unsigned char* s = srcs[cur_src.load()].data();
+            const size_t from = (size_t)lane * spl * per;
+            size_t upto = ((size_t)lane * spl + cnt) * per;
+            if (upto > total) upto = total;
+            if (from >= upto) continue;
+            if (gen == cur_gen.load() && memcmp(dst + from, s + from, upto - from) != 0 && gen == cur_gen.load()) errors++;
+          }
         }
       });
       uint32_t gen = 0;
@@ -58,13 +62,23 @@ HARNESS = textwrap.dedent(r'''
         const int si = it & 3;
         for (size_t k = 0; k < total; k += 97) srcs[si][k] = (unsigned char)(it + k);
         gen = (gen + 1) & 0x00FFFFFFu; if (gen == 0) gen = 1;
-        cur_src = si; cur_per = per; cur_nsl = nsl;
+        uint32_t spl = 1;
+        const uint32_t lanes = stage_plan(helper, nsl, &spl);
+        if (lanes < 1 || lanes > (uint32_t)threads || (uint64_t)lanes * spl < nsl || (uint64_t)(lanes - 1) * spl >= nsl) {
+          printf("bad plan: nsl %u lanes %u spl %u\n", nsl, lanes, spl); return 1;
+        }
+        cur_src = si; cur_per = per; cur_nsl = nsl; cur_spl = spl;
         cur_gen = gen;
-        __atomic_store_n(word, gen << 8, __ATOMIC_RELEASE);
-        stage_slices(helper, dst, srcs[si].data(), per, total, nsl, gen, word);
-        __atomic_store_n(word, (gen << 8) | nsl, __ATOMIC_RELEASE);
+        for (uint32_t k = 0; k < lanes; ++k) __atomic_store_n(words + k * CL_STAGE_WORD_STRIDE, gen << 8, __ATOMIC_RELEASE);
+        stage_slices(helper, dst, srcs[si].data(), per, total, nsl, gen, words);
         if (memcmp(dst, srcs[si].data(), total) != 0) { printf("final mismatch at %d\n", it); return 1; }
-        if ((*word & 255u) != nsl) { printf("count %u != %u\n", *word & 255u, nsl); return 1; }
+        uint32_t sum = 0;
+        for (uint32_t k = 0; k < lanes; ++k) {
+          const uint32_t w = words[k * CL_STAGE_WORD_STRIDE];
+          if ((w >> 8) != gen || (w & 255u) != stage_lane_count(k, spl, nsl)) { printf("lane %u count %u\n", k, w & 255u); return 1; }
+          sum += w & 255u;
+        }
+        if (sum != nsl) { printf("count %u != %u\n", sum, nsl); return 1; }
       }
       stop = 1;
       checker.join();
@@ -75,7 +89,7 @@ HARNESS = textwrap.dedent(r'''
 ''')
 
 
-@pytest.mark.parametrize("threads", [1, 2])
+@pytest.mark.parametrize("threads", [1, 2, 3, 4])
 def test_staging_protocol_under_stress(tmp_path, threads):
     gxx = shutil.which("g++")
     if gxx is None:
