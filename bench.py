@@ -353,9 +353,9 @@ def run_b200(args):
         }
 
     # ---- e2e: the SB3-facing VecEnv API with host buffers -------------------------------------
-    # Per control interval: the step's actions travel host->device from PINNED host memory (the
-    # env's own staging buffer, which a host-side policy writes into), the kernel runs, and
-    # obs / reward / done travel device->host; `infos` bookkeeping for finished episodes included.
+    # Per control interval: the caller's (pageable) action array is staged into pinned host memory by the
+    # library's staging lanes while the step kernel, already launched, reads it slice by slice; obs / reward /
+    # done travel device->host; `infos` bookkeeping for finished episodes included.
     e2e = None
     if not args.no_e2e:
         env = BatchedChaosVecEnv(args.kind, N, device=dev, seed=0, env_id_base=slab.env_id_base,

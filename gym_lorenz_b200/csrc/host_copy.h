@@ -116,8 +116,11 @@ static void* copy_worker_main(void* arg) {
 }
 
 // Copy threads this process should use for one env batch: CHAOS_B200_COPY_THREADS=1..4 decides; otherwise by
-// the cores this process may run on, shared between the ranks of the node (LOCAL_WORLD_SIZE, torchrun): four
-// threads from 12 cores per rank, three from 8, two from 4, else one.
+// the cores this process may run on, shared between the ranks of the node (LOCAL_WORLD_SIZE, torchrun): three
+// threads from 8 cores per rank, two from 4, else one.  Measured at 65,536 envs, 16 cores, in-process A/B
+// (profiles/r02l_e2e_lanes_*.jsonl): lorenz_rk4 84-88 / 70.5-74 / 69.4-71.1 / 69.0-71.7 us per step with
+// 1 / 2 / 3 / 4 lanes (actions already pinned: 63.5); hr_sync 70-72 with 2 or 4; pmsm_sync 69-71 with 2 or 4 --
+// a fourth thread buys nothing.
 static int copy_threads_default(void) {
   if (const char* ov = getenv("CHAOS_B200_COPY_THREADS")) {
     const int t = atoi(ov);
@@ -127,7 +130,7 @@ static int copy_threads_default(void) {
   CPU_ZERO(&set);
   int cores = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
   if (const char* lw = getenv("LOCAL_WORLD_SIZE")) { const int k = atoi(lw); if (k > 1) cores /= k; }
-  return cores >= 12 ? 4 : (cores >= 8 ? 3 : (cores >= 4 ? 2 : 1));
+  return cores >= 8 ? 3 : (cores >= 4 ? 2 : 1);
 }
 
 // nullptr: single-threaded staging (one lane).  Never started for batches whose actions are under 64 KB.
