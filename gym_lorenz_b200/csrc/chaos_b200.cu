@@ -86,6 +86,7 @@ struct HostStage {
   uint8_t* d_warp_done;  // device copy for CL_HOST_DMA (travels with the result block)
   size_t wd_bytes;
   struct CopyHelper* helper;   // helper threads of the staging lanes (nullptr: single-threaded staging)
+  int relay_kernel;            // 1: k_relay on the side stream (a second launch per step; CHAOS_B200_RELAY=kernel), 0: block 0 of the step kernel
   cl_buffers redo_buf;         // buffers of the step in flight
   int64_t streamed_fallbacks;  // streamed steps called off by k_relay and redone as zero-copy steps
 };
@@ -304,54 +305,11 @@ static int fill_params(cl_ctx* ctx, const cl_buffers* buf, const cl_io* io, KPar
 
 __global__ void k_advance_step(uint64_t* step, uint64_t count) { *step += count; }
 
-// Streamed host mode.  Mirrors the pinned progress words of the staging lanes ((gen << 8) | slices of that lane
-// staged so far; host_copy.h) into device memory until every lane is complete: relay thread k reads lane k's
-// word (the system-scope reads of the lanes are in flight together) and is the only writer of its device
-// copy.  The warp is also the judge of whether streaming works at all: if NO lane has published anything
-// within 20 ms of its start, the CPU is evidently not running concurrently with the GPU work (a profiler or
-// CUDA_LAUNCH_BLOCKING made the launches synchronous, so the staging loop only starts after the kernels have
-// finished).  It then writes count 255 = "called off" to every lane: every block of the step kernel exits
-// before storing anything (no block can have passed its wait: nothing was mirrored), *host_err = 2 tells
-// cl_step_host_wait to redo the step from the (by then complete) staging buffer without streaming and to
-// keep this context out of streamed mode.  The decision is a warp vote taken in the same loop iteration by
-// all lanes, so "called off" and "a lane was mirrored" exclude each other.
-// *host_err = 1: published partially and then nothing for 2 s -- unrecoverable, reported as an error.
+// Streamed host mode: the relay (cl::relay_lanes, kernels_common.cuh) as a kernel of its own on the side stream
+// (CHAOS_B200_RELAY=kernel); by default it runs as block 0 of the step kernel.
 __global__ void k_relay(const uint32_t* host_words, uint32_t* dev_words, uint32_t gen, uint32_t lanes, uint32_t spl,
                         uint32_t nslices, uint32_t* host_err) {
-  const uint32_t k = threadIdx.x;
-  if (k >= lanes) return;
-  const unsigned mask = lanes >= 32u ? 0xffffffffu : ((1u << lanes) - 1u);
-  const uint32_t first = k * spl;
-  const uint32_t want = first >= nslices ? 0u : (nslices - first < spl ? nslices - first : spl);
-  const uint32_t* host_word = host_words + (size_t)k * CL_STAGE_WORD_STRIDE;
-  uint32_t last = 0, polls = 0;
-  uint64_t t0 = 0, t1 = 0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (;;) {
-    if (last < want) {
-      const uint32_t v = cl::ld_acquire_sys_u32(host_word);   // one system-scope read per lane per ~4 us: the only ones on the GPU
-      if ((v >> 8) == gen && (v & 255u) > last && (v & 255u) <= want) {
-        last = v & 255u;
-        *(volatile uint32_t*)(dev_words + k) = v;
-        __threadfence();
-      }
-    }
-    if (__all_sync(mask, last >= want)) return;
-    if ((++polls & 7u) == 0u) {
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      const uint64_t waited = __shfl_sync(mask, t1 - t0, 0);
-      const bool none = !__any_sync(mask, last > 0u);
-      if ((none && waited > 20000000ull) || waited > 2000000000ull) {
-        if (last < want) {
-          *(volatile uint32_t*)(dev_words + k) = (gen << 8) | 255u;
-          __threadfence();
-        }
-        __syncwarp(mask);
-        if (k == 0) *host_err = none ? 2u : 1u;
-        return;
-      }
-    }
-  }
+  cl::relay_lanes(host_words, dev_words, gen, lanes, spl, nslices, host_err);
 }
 
 static int launch(cl_ctx* ctx, const KParams& p_in, int mode, cudaStream_t st) {
@@ -673,6 +631,7 @@ static int host_stage_init(cl_ctx* ctx) {
   }
   if (const char* ov = getenv("CHAOS_B200_HOST_SLICES")) { const int k = atoi(ov); if (k >= 1 && k <= 64) h.slices = k; }
   h.helper = copy_helper_start(N * A * sizeof(float));
+  { const char* ov = getenv("CHAOS_B200_RELAY"); h.relay_kernel = (ov && !strcmp(ov, "kernel")) ? 1 : 0; }
   h.ready = true;
   return CL_OK;
 }
@@ -737,8 +696,8 @@ static int host_step_launch(cl_ctx* ctx, cudaStream_t st, const cl_buffers* buf,
   if (host_out) { memset(s.warp_done, 0, h.wd_bytes); p.warp_done = s.warp_done; p.host_rows = 1; }
   else { CU(cudaMemsetAsync(h.d_warp_done, 0, h.wd_bytes, st)); p.warp_done = h.d_warp_done; }
   if (mode == CL_HOST_STREAMED) {
-    // 1. launch k_relay (side stream: mirrors the pinned "slices staged" word into device memory) and
-    //    the step kernel, whose blocks wait for the slice they read;
+    // 1. launch the step kernel, whose blocks wait for the slice they read; its block 0 is the relay that mirrors
+    //    the pinned "slices staged" words into device memory (or k_relay on the side stream, CHAOS_B200_RELAY=kernel);
     // 2. stage the caller's array into the pinned buffer: the slices are dealt out to staging lanes (one copy
     //    thread each, host_copy.h), every lane publishes its count after each slice.  The final counts are
     //    stored whatever happens in between, so both kernels always terminate (and their waits are bounded anyway).
@@ -760,10 +719,14 @@ static int host_step_launch(cl_ctx* ctx, cudaStream_t st, const cl_buffers* buf,
     };
     p.act_ready = h.d_ready; p.act_gen = h.gen; p.act_slice_envs = (int32_t)per; p.act_lane_slices = (int32_t)spl;
     p.host_err = h.h_err;
-    k_relay<<<1, 32, 0, h.side>>>(h.h_ready, h.d_ready, h.gen, lanes, spl, nsl, h.h_err);
-    if (cudaGetLastError() != cudaSuccess) {
-      publish_all();
-      return fail(ctx, CL_ECUDA, "relay kernel launch failed");
+    if (h.relay_kernel) {
+      k_relay<<<1, 32, 0, h.side>>>(h.h_ready, h.d_ready, h.gen, lanes, spl, nsl, h.h_err);
+      if (cudaGetLastError() != cudaSuccess) {
+        publish_all();
+        return fail(ctx, CL_ECUDA, "relay kernel launch failed");
+      }
+    } else {
+      p.act_host_words = h.h_ready; p.act_lanes = (int32_t)lanes; p.act_nslices = (int32_t)nsl;
     }
     r = launch(ctx, p, cl::MODE_STEP, st);
     if (r == CL_OK)

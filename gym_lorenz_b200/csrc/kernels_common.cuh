@@ -53,6 +53,9 @@ struct KParams {
   uint32_t act_gen;
   int32_t act_slice_envs;
   int32_t act_lane_slices;   // slices per staging lane; lane k's progress word is act_ready[k]
+  // in-kernel relay (block 0 of the step kernel mirrors the pinned progress words itself; nullptr: k_relay does, on a side stream)
+  const uint32_t* act_host_words;
+  int32_t act_lanes, act_nslices;
   uint32_t* host_err;
   // rollout
   int32_t T;
@@ -482,6 +485,59 @@ __device__ __forceinline__ void synth_action(const KParams& p, const Stream& rng
   for (int c = 0; c < E::ACT; ++c) a[c] = p.synth_amp * (2.0f * u01_24(w[c & 3]) - 1.0f);
 }
 
+// ---- streamed host mode: the relay ----------------------------------------------------------
+// Mirrors the pinned progress words of the staging lanes ((gen << 8) | slices of that lane staged so far;
+// host_copy.h) into device memory until every lane is complete: relay thread k reads lane k's word (the
+// system-scope reads of the lanes are in flight together) and is the only writer of its device copy.  The
+// warp is also the judge of whether streaming works at all: if NO lane has published anything within 20 ms of
+// its start, the CPU is evidently not running concurrently with the GPU work (a profiler or
+// CUDA_LAUNCH_BLOCKING made the launches synchronous, so the staging loop only starts after the kernels have
+// finished).  It then writes count 255 = "called off" to every lane: every block of the step kernel exits
+// before storing anything (no block can have passed its wait: nothing was mirrored), *host_err = 2 tells
+// cl_step_host_wait to redo the step from the (by then complete) staging buffer without streaming and to
+// keep this context out of streamed mode.  The decision is a warp vote taken in the same loop iteration by
+// all lanes, so "called off" and "a lane was mirrored" exclude each other.
+// *host_err = 1: published partially and then nothing for 2 s -- unrecoverable, reported as an error.
+// Runs either as block 0 of the step kernel itself (KParams::act_host_words, one launch per step) or as the
+// one-warp kernel k_relay on a side stream.
+static __device__ __noinline__ void relay_lanes(const uint32_t* host_words, uint32_t* dev_words, uint32_t gen, uint32_t lanes,
+                                         uint32_t spl, uint32_t nslices, uint32_t* host_err) {
+  const uint32_t k = threadIdx.x;
+  if (k >= lanes) return;
+  const unsigned mask = lanes >= 32u ? 0xffffffffu : ((1u << lanes) - 1u);
+  const uint32_t first = k * spl;
+  const uint32_t want = first >= nslices ? 0u : (nslices - first < spl ? nslices - first : spl);
+  const uint32_t* host_word = host_words + (size_t)k * 16u;   // CL_STAGE_WORD_STRIDE
+  uint32_t last = 0, polls = 0;
+  uint64_t t0 = 0, t1 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    if (last < want) {
+      const uint32_t v = ld_acquire_sys_u32(host_word);   // one system-scope read per lane per ~4 us: the only ones on the GPU
+      if ((v >> 8) == gen && (v & 255u) > last && (v & 255u) <= want) {
+        last = v & 255u;
+        *(volatile uint32_t*)(dev_words + k) = v;
+        __threadfence();
+      }
+    }
+    if (__all_sync(mask, last >= want)) return;
+    if ((++polls & 7u) == 0u) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      const uint64_t waited = __shfl_sync(mask, t1 - t0, 0);
+      const bool none = !__any_sync(mask, last > 0u);
+      if ((none && waited > 20000000ull) || waited > 2000000000ull) {
+        if (last < want) {
+          *(volatile uint32_t*)(dev_words + k) = (gen << 8) | 255u;
+          __threadfence();
+        }
+        __syncwarp(mask);
+        if (k == 0) *host_err = none ? 2u : 1u;
+        return;
+      }
+    }
+  }
+}
+
 // ---- the static step / rollout kernel: thread i owns env i for the whole launch ----------
 
 // Resident 256-thread blocks per SM the SINGLE-STEP kernel is compiled for (0 = leave it to ptxas).
@@ -505,7 +561,16 @@ __global__ void __launch_bounds__(256, ROLL ? 0 : StepMinBlocks<E>::value) k_ste
     if (threadIdx.x < CL_NSTATS) s_stats[threadIdx.x] = 0.0;
     __syncthreads();
   }
-  const int64_t i = p.i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // streamed host mode with the relay inside this launch: block 0 is the relay (dispatched first, so it is
+  // resident whatever the grid size), env blocks follow
+  const bool relay_inside = !ROLL && p.act_host_words != nullptr;   // block-uniform
+  if (relay_inside && blockIdx.x == 0) {
+    if (threadIdx.x < 32)
+      relay_lanes(p.act_host_words, const_cast<uint32_t*>(p.act_ready), p.act_gen, (uint32_t)p.act_lanes,
+                  (uint32_t)p.act_lane_slices, (uint32_t)p.act_nslices, p.host_err);
+    return;
+  }
+  const int64_t i = p.i_begin + (int64_t)(blockIdx.x - (relay_inside ? 1u : 0u)) * blockDim.x + threadIdx.x;
   const bool live = i < p.n;
   const unsigned lane = threadIdx.x & 31u;
   float* sm_rows = sm_rows_all + (threadIdx.x >> 5) * (32 * E::OBS);
@@ -1163,9 +1228,10 @@ cudaError_t launch_env(const KParams& p_in, int mode, cudaStream_t st, int block
   p.host_plain_out = nullptr;
   const size_t row_smem = p.rows_fast ? (size_t)(block / 32) * 32 * E::OBS * sizeof(float) : 0;
   const unsigned grid = (unsigned)((p.n - p.i_begin + block - 1) / block);  // i_begin != 0 only for MODE_STEP
+  const unsigned step_grid = grid + ((mode == MODE_STEP && p.act_host_words != nullptr) ? 1u : 0u);   // + the relay block
   switch (mode) {
     // dynamic smem only when observations go out as contiguous float32 rows (row-store staging)
-    case MODE_STEP: k_step<E, false><<<grid, block, row_smem, st>>>(p); break;
+    case MODE_STEP: k_step<E, false><<<step_grid, block, row_smem, st>>>(p); break;
     case MODE_ROLLOUT:
       if (plain) k_step<E, true, HAS_PLAIN><<<grid, block, row_smem, st>>>(p);
       else k_step<E, true><<<grid, block, row_smem, st>>>(p);

@@ -284,17 +284,22 @@ def test_host_step_modes_give_identical_results(kind):
     modes = [("dma", 1), ("zerocopy", 1), ("pipelined", 2), ("pipelined", 3), ("pipelined", 7), ("pipelined", 64),
              ("streamed", 1), ("streamed", 3), ("streamed", 16), ("streamed", 64),
              # staging lanes (copy threads): 1 .. 4, slice counts that do and do not divide by the lanes
-             ("streamed", 16, 1), ("streamed", 5, 2), ("streamed", 16, 3), ("streamed", 2, 4), ("streamed", 37, 4)]
+             ("streamed", 16, 1), ("streamed", 5, 2), ("streamed", 16, 3), ("streamed", 2, 4), ("streamed", 37, 4),
+             # negative: the relay as its own kernel on the side stream instead of block 0 of the step kernel
+             ("streamed", 16, -1), ("streamed", 37, -3)]
     rng = np.random.default_rng(5)
     ref = None
     for mode, k, *threads in modes:
-        if threads:
-            os.environ["CHAOS_B200_COPY_THREADS"] = str(threads[0])
-        else:
-            os.environ.pop("CHAOS_B200_COPY_THREADS", None)
-        env = BatchedChaosVecEnv(kind, n, seed=3, max_episode_steps=4)
-        env.batch.set_host_mode(mode, k)        # creates the staging context (reads the variable)
         os.environ.pop("CHAOS_B200_COPY_THREADS", None)
+        os.environ.pop("CHAOS_B200_RELAY", None)
+        if threads:
+            os.environ["CHAOS_B200_COPY_THREADS"] = str(abs(threads[0]))
+            if threads[0] < 0:
+                os.environ["CHAOS_B200_RELAY"] = "kernel"
+        env = BatchedChaosVecEnv(kind, n, seed=3, max_episode_steps=4)
+        env.batch.set_host_mode(mode, k)        # creates the staging context (reads the variables)
+        os.environ.pop("CHAOS_B200_COPY_THREADS", None)
+        os.environ.pop("CHAOS_B200_RELAY", None)
         a_rng = np.random.default_rng(11)
         lo, hi = env.action_space.low, env.action_space.high
         trace = [env.reset().copy()]

@@ -14,7 +14,8 @@ if len(sys.argv) > 2:
     variants = [tuple(int(x) for x in v.split(":")) for v in sys.argv[2].split(",")]
 for rep in range(3):
     for th, sl in variants:
-        os.environ["CHAOS_B200_COPY_THREADS"] = str(th)
+        os.environ["CHAOS_B200_COPY_THREADS"] = str(abs(th))
+        os.environ["CHAOS_B200_RELAY"] = "kernel" if th < 0 else "block"      # negative thread count: k_relay as its own launch
         env = BatchedChaosVecEnv(kind, N)
         env.batch.set_host_mode("streamed", sl)
         env.reset()
@@ -25,7 +26,7 @@ for rep in range(3):
         for k in range(400):
             env.step(acts[k % 8])
         torch.cuda.synchronize()
-        row = {"kind": kind, "envs": N, "rep": rep, "copy_threads": th, "slices": sl,
+        row = {"kind": kind, "envs": N, "rep": rep, "copy_threads": abs(th), "relay": "kernel" if th < 0 else "block0", "slices": sl,
                "us_per_step": round((time.perf_counter() - t0) / 400 * 1e6, 2)}
         if (th, sl) == variants[-1]:        # the floor: actions already in the pinned staging buffer
             env.batch.host_action_buffer()[:] = acts[0]
