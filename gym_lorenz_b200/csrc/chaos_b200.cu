@@ -562,12 +562,17 @@ extern "C" int cl_block_size(const cl_ctx* ctx) { return ctx ? ctx->block : 0; }
 // never wins, streamed wins once the staging copy is long enough to hide a relay launch behind.
 static void host_mode_default(int kind, int64_t n, int* mode, int* slices) {
   const int64_t action_bytes = n * (int64_t)kLayouts[kind].act_dim * 4;
-  if (action_bytes >= 384 * 1024) {
-    *mode = CL_HOST_STREAMED;          // 65,536 envs: 94-99 vs 118 us (lorenz_rk4), 83-85 vs 95 (pmsm_sync), 137-139 vs 150 (hr_sync)
+  // With the relay inside the step kernel streaming costs no second launch, so it pays from smaller arrays than
+  // with the separate relay kernel (384 KB then).  A-B-A-B on one env, caller-owned array, us per step zero-copy vs
+  // streamed (profiles/r02f4_e2e_small_ab.jsonl, r02f3_e2e_host_modes.jsonl): 48 KB of actions 32.5-35.3 vs 33.3-35.7,
+  // 64 KB 39.3 vs 40.4, 96 KB 40.7-42.5 vs 39.1-40.5, 128 KB 36.3-36.9 vs 33.4-33.9, 192 KB 38.9-41.9 vs 34.1-36.9,
+  // 768 KB 109.7 vs 64.8, 3 MB 377 vs 195.
+  if (action_bytes >= 96 * 1024) {
+    *mode = CL_HOST_STREAMED;
     int k = (int)(n / 2048);           // finer slices keep paying up to the relay's poll period (~4 us of staging)
     *slices = k < 1 ? 1 : (k > 64 ? 64 : k);
   } else {
-    *mode = CL_HOST_ZEROCOPY;          // 4,096 / 16,384 envs: the relay launch costs more (2-6 us) than the overlap returns
+    *mode = CL_HOST_ZEROCOPY;
     *slices = 1;
   }
 }

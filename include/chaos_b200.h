@@ -241,19 +241,20 @@ int cl_host_action_staging(cl_ctx* ctx, float** action_pinned);
 /* zero-copy variant of the host path: the step kernel reads actions from / writes results to the
  * pinned (UVA-mapped) host buffers directly instead of DMA copies around it */
 int cl_host_set_zero_copy(cl_ctx* ctx, int enable);
-/* how cl_step_host_async moves the data (default: STREAMED with one slice per 8,192 envs, chosen per
- * (kind, batch size) by host_mode_default() in csrc/chaos_b200.cu from the measured table
- * profiles/r02_e2e_host_modes.jsonl; CHAOS_B200_HOST_MODE=dma|zerocopy|pipelined|streamed overrides):
+/* how cl_step_host_async moves the data (default: STREAMED with one slice per 2,048 envs from 96 KB of
+ * actions per step, ZEROCOPY below; chosen by host_mode_default() in csrc/chaos_b200.cu from the measured
+ * tables profiles/r02f4_e2e_small_ab.jsonl, r02f3_e2e_host_modes.jsonl; CHAOS_B200_HOST_MODE=dma|zerocopy|pipelined|streamed overrides):
  *   CL_HOST_DMA        H2D copy of the actions -> step kernel -> one D2H copy of obs|reward|done
  *   CL_HOST_ZEROCOPY   one launch; the kernel reads / writes the pinned host buffers itself
  *   CL_HOST_PIPELINED  `slices` env slices alternate over two streams: per slice a DMA copy of its
  *                      actions, then its step kernel writing the results to pinned host memory, so
  *                      upstream and downstream PCIe traffic of neighbouring slices overlap.
  *   CL_HOST_STREAMED   ZEROCOPY whose single launch is issued BEFORE the caller's action array is staged
- *                      into pinned memory: the staging loop publishes the buffer slice by slice
- *                      (generation flags in pinned memory) and each block of the kernel waits for the
- *                      slice it reads, so the host memcpy, the launch latency and the PCIe traffic of
- *                      the slices already published overlap.  Falls back to ZEROCOPY when the caller
+ *                      into pinned memory: up to four staging lanes (copy threads, CHAOS_B200_COPY_THREADS)
+ *                      publish the buffer slice by slice (generation words in pinned memory, one per
+ *                      lane), block 0 of the kernel mirrors those words into device memory and each
+ *                      other block waits for the slice it reads, so the host memcpy, the launch latency
+ *                      and the PCIe traffic of the slices already published overlap.  Falls back to ZEROCOPY when the caller
  *                      passes the pinned staging buffer itself or the context is in graph mode.
  * Results are identical in all modes (same kernel, same per-env Philox streams). */
 enum { CL_HOST_DMA = 0, CL_HOST_ZEROCOPY = 1, CL_HOST_PIPELINED = 2, CL_HOST_STREAMED = 3 };
