@@ -22,8 +22,14 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)   # absent in CPU-only builds
+
+
 def _stream(dev: torch.device):
-    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    """torch's current stream on `dev` as a raw cudaStream_t (see ChaosBatch._stream)."""
+    if _RAW_STREAM is not None and dev.index is not None:
+        return _RAW_STREAM(dev.index)
+    return torch.cuda.current_stream(dev).cuda_stream
 
 
 def gae(rewards: torch.Tensor, values: torch.Tensor, episode_starts: torch.Tensor, last_values: torch.Tensor,
