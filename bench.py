@@ -411,7 +411,12 @@ def run_b200(args):
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample, v1, _ = cpu_arm(args, budget_s=12.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                                    "single_core_value": v1}
+                                    "single_core_value": v1,
+                                    "note": "C/OpenMP restatement of the reference's scheme (oracle/chaos_oracle.c); the "
+                                            "unmodified Python reference cannot travel to the GPU box -- in the build "
+                                            "container its env classes ran at 1.2e4-2.5e4 steps/s on one core "
+                                            "(profiles/r01_reference_python_container.json), ~100x below this port's "
+                                            "single-core rate, so every ratio against this baseline is conservative"}
         print(json.dumps(line), flush=True)
     batch.close()
     if world > 1:
