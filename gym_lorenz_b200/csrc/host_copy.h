@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 // Staging copy caller array -> pinned buffer.  Optional variant with non-temporal (streaming) stores (AVX2;
 // memcpy for the unaligned edges; ends with a store fence: the "slice staged" word that follows must not
@@ -129,7 +130,10 @@ static int copy_threads_default(void) {
   cpu_set_t set;
   CPU_ZERO(&set);
   int cores = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
-  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) { const int k = atoi(lw); if (k > 1) cores /= k; }
+  // an unpinned rank shares the machine with the other local ranks; a rank already pinned to its share
+  // (distributed.pin_rank_to_cores) reports that share itself
+  const long online = sysconf(_SC_NPROCESSORS_ONLN);
+  if (const char* lw = getenv("LOCAL_WORLD_SIZE")) { const int k = atoi(lw); if (k > 1 && (long)cores >= online) cores /= k; }
   return cores >= 8 ? 3 : (cores >= 4 ? 2 : 1);
 }
 
