@@ -8,6 +8,7 @@ them to a policy directly, or export with `torch.utils.dlpack.to_dlpack`).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -429,6 +430,28 @@ class ChaosBatch:
     @property
     def d2h_bytes_per_step(self) -> int:
         return self.lib.cl_host_d2h_bytes(self.ctx)
+
+
+def _install_nvtx_ranges() -> None:
+    """CHAOS_B200_NVTX=1: every ChaosBatch entry point that launches work runs inside an NVTX range
+    ("chaos.step", "chaos.rollout", "chaos.step_host_async", ...), so a profile can be cut per call
+    (`ncu --nvtx --nvtx-include "chaos.rollout/" ...`, Nsight Systems timelines).  Off by default: the
+    wrappers cost ~1 us per call."""
+    def ranged(fn, name):
+        def wrapper(*a, **k):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+        return wrapper
+    for name in ("reset", "step", "rollout", "derivatives", "step_host_async", "step_host_wait", "reset_host"):
+        setattr(ChaosBatch, name, ranged(getattr(ChaosBatch, name), "chaos." + name))
+
+
+if os.environ.get("CHAOS_B200_NVTX") == "1":
+    _install_nvtx_ranges()
 
 
 def measure_fma_peak(device: int = 0, dtype_bytes: int = 8, seconds: float = 0.5) -> float:

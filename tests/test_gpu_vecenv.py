@@ -395,3 +395,34 @@ def test_streamed_host_mode_survives_synchronous_launches(tmp_path):
     assert out[("streamed", "1")]["hash"] == out[("zerocopy", "0")]["hash"]
     assert out[("streamed", "0")]["fallbacks"] == 0
     assert out[("streamed", "1")]["fallbacks"] == 1
+
+
+def test_nvtx_ranges_option(tmp_path):
+    """CHAOS_B200_NVTX=1 wraps the launching entry points in NVTX ranges; results do not change."""
+    import subprocess
+    import sys
+    script = tmp_path / "run.py"
+    script.write_text(
+        "import sys, hashlib\n"
+        f"sys.path.insert(0, {str(H.os.path.dirname(H.os.path.dirname(H.os.path.abspath(__file__))))!r})\n"
+        "import numpy as np, torch\n"
+        "from gym_lorenz_b200.core import ChaosBatch\n"
+        "from gym_lorenz_b200.vec_env import BatchedChaosVecEnv\n"
+        "env = BatchedChaosVecEnv('hr_sync', 3000, seed=3)\n"
+        "env.reset()\n"
+        "rng = np.random.default_rng(1)\n"
+        "h = hashlib.sha256()\n"
+        "for t in range(4):\n"
+        "    obs, rew, done, infos = env.step(rng.uniform(-1, 1, (3000, 2)).astype(np.float32))\n"
+        "    h.update(obs.tobytes()); h.update(rew.tobytes())\n"
+        "out = env.batch.rollout(3)\n"
+        "h.update(out['reward'].cpu().numpy().tobytes())\n"
+        "print(h.hexdigest(), ChaosBatch.step.__name__, hasattr(ChaosBatch.step, '__wrapped__') or 'wrapper' in repr(ChaosBatch.step))\n")
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(H.os.environ, CHAOS_B200_NVTX=flag)
+        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines()[-1].split())
+    assert outs[0][0] == outs[1][0]                     # same results
+    assert outs[0][2] == "False" and outs[1][2] == "True"   # ranges only when asked for
