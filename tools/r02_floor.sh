@@ -1,4 +1,5 @@
 #!/bin/bash
+# Key-stream GPU tests, breakdown of a host-buffer step at 65,536 / 256 envs, bench line (profiles/r02m_*)
 O=gpurun_out
 T="timeout -k 5"
 $T 300 python -m pytest tests/test_keystream.py -q -m gpu -x > $O/pytest_keystream.log 2>&1; echo "keystream rc=$?"; tail -3 $O/pytest_keystream.log

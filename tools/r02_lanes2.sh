@@ -1,5 +1,7 @@
 #!/bin/bash
-# Helpers-first staging (stage_begin before the launches): parity, sync-launch behaviour, in-process A/B, stream-query sync A/B
+# Helpers-first staging (stage_begin before the launches): parity, sync-launch behaviour, in-process A/B, stream-query sync A/B.
+# Both variants measured worse and were reverted (dead ends 4 and 5; results: profiles/r02n_*); the script is kept
+# as the record of what was run -- on the current tree it measures the shipped scheme.
 O=gpurun_out
 T="timeout -k 5"
 $T 600 python -m pytest tests/test_gpu_vecenv.py -q -m gpu -x > $O/pytest_lanes2.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_lanes2.log
