@@ -273,7 +273,7 @@ def test_graph_mode_replay_equals_eager_stepping(kind):
     b.close(); e.close()
 
 
-@pytest.mark.parametrize("kind", ["lorenz_rk4", "hr_sync", "pmsm_sync"])
+@pytest.mark.parametrize("kind", ["lorenz_rk4", "hr_sync", "pmsm_sync", "memristive4_pair"])   # the last one: per-block episode statistics
 def test_host_step_modes_give_identical_results(kind):
     """DMA chain, zero-copy, the sliced two-stream pipeline and the streamed mode (kernel launched before
     the caller's array is staged, blocks wait for their slice's generation flag) are the same computation: every
