@@ -12,6 +12,7 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -52,15 +53,19 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         ("tu_rl_ops.cu", ["-fmad=false"]),
         ("chaos_b200.cu", []),
     ]
-    objs = []
-    for src, extra in units:
+    def compile_unit(unit):
+        src, extra = unit
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True)
-        objs.append(obj)
+        return obj
+
+    # the four translation units are independent: compile them side by side (55 s -> the longest unit)
+    with ThreadPoolExecutor(max_workers=len(units)) as pool:
+        objs = list(pool.map(compile_unit, units))
     cmd = [nvcc, *ARCH, "-shared", "-cudart", "static", "-o", LIB, *objs]
     subprocess.run(cmd, check=True)
     return LIB
